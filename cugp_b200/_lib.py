@@ -1,0 +1,104 @@
+"""ctypes binding of libcugp.so (include/cugp.h).  The CUDA library is the product: if it is missing or
+no CUDA device is visible, calls fail loudly -- there is no CPU fallback anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcugp.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_NODEVICE = 0, 1, 2, 3, 4
+dp = C.POINTER(C.c_double)
+EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, dp, dp, dp)
+
+
+class CugpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"cugp error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/cugp.h declares
+SIGNATURES = {
+    "cugp_version": (C.c_char_p, []),
+    "cugp_last_error": (C.c_char_p, []),
+    "cugp_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "cugp_set_device": (C.c_int, [C.c_int]),
+    "cugp_launch_count": (C.c_long, []),
+    "cugp_launch_count_reset": (None, []),
+    "cugp_covsum_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "cugp_covsum_destroy": (C.c_int, [C.c_void_p]),
+    "cugp_covsum_set_loghyper": (C.c_int, [C.c_void_p, dp]),
+    "cugp_covsum_get_loghyper": (C.c_int, [C.c_void_p, dp]),
+    "cugp_covsum_K_train": (C.c_int, [C.c_void_p, dp, dp]),
+    "cugp_covsum_k_test": (C.c_int, [C.c_void_p, dp, dp, dp]),
+    "cugp_covsum_loglik": (C.c_int, [C.c_void_p, dp, dp, dp]),
+    "cugp_covsum_grad": (C.c_int, [C.c_void_p, dp, dp, dp]),
+    "cugp_covsum_predict": (C.c_int, [C.c_void_p, dp, dp, dp, C.c_int, dp, dp]),
+    "cugp_nlpp": (C.c_int, [dp, dp, dp, C.c_int, dp]),
+    "cugp_covsum_cg_solve": (C.c_int, [C.c_void_p, dp, dp, dp, C.c_int, C.POINTER(C.c_int)]),
+    "cugp_covsum_rprop_solve": (C.c_int, [C.c_void_p, dp, dp]),
+    "cugp_cg_minimize": (C.c_int, [EVAL_FN, C.c_void_p, dp, dp, C.c_int, C.POINTER(C.c_int)]),
+    "cugp_rprop_minimize": (C.c_int, [EVAL_FN, C.c_void_p, dp, C.POINTER(C.c_int)]),
+    "cugp_covsum_set_data": (C.c_int, [C.c_void_p, dp, dp]),
+    "cugp_covsum_loglik_resident": (C.c_int, [C.c_void_p, dp]),
+    "cugp_covsum_grad_resident": (C.c_int, [C.c_void_p, dp]),
+    "cugp_covsum_scalars_resident": (C.c_int, [C.c_void_p, dp]),
+    "cugp_covsum_alpha_resident": (C.c_int, [C.c_void_p, dp]),
+    "cugp_covsum_factorize_resident": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "cugp_cholesky": (C.c_int, [dp, dp, C.c_int]),
+    "cugp_chol_and_det": (C.c_int, [dp, dp, C.c_int, dp, dp]),
+    "cugp_kinv_y": (C.c_int, [dp, dp, dp, C.c_int]),
+    "cugp_k_inverse": (C.c_int, [dp, dp, C.c_int]),
+    "cugp_bcm_create": (C.c_int, [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "cugp_bcm_destroy": (C.c_int, [C.c_void_p]),
+    "cugp_bcm_set_loghyper": (C.c_int, [C.c_void_p, dp]),
+    "cugp_bcm_get_loghyper": (C.c_int, [C.c_void_p, dp]),
+    "cugp_bcm_loglik_grad_local": (C.c_int, [C.c_void_p, C.c_int, dp]),
+    "cugp_bcm_local_experts": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), dp]),
+    "cugp_bcm_predict_moments_dev": (C.c_int, [C.c_void_p, dp, C.c_int, C.c_void_p]),
+    "cugp_bcm_predict_moments": (C.c_int, [C.c_void_p, dp, C.c_int, dp]),
+    "cugp_poe_finalize_dev": (C.c_int, [C.c_void_p, C.c_int, dp, dp]),
+    "cugp_poe_finalize": (C.c_int, [dp, C.c_int, dp, dp]),
+    "cugp_bcm_predict": (C.c_int, [C.c_void_p, dp, C.c_int, dp, dp]),
+    "cugp_probe_fp64_peak": (C.c_int, [C.c_float, dp, dp]),
+    "cugp_probe_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, dp]),
+    "cugp_debug_gemm": (C.c_int, [dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, dp]),
+    "cugp_probe_copy": (C.c_int, [C.c_size_t, C.c_int, dp]),
+}
+
+
+def lib():
+    """Load libcugp.so.  Raises if it has not been built: the CUDA extension IS the product."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m cugp_b200.build` (nvcc, sm_100a). "
+                "cugp_b200 has no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise CugpError(rc, lib().cugp_last_error().decode())
+
+
+def f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ptr(a: np.ndarray):
+    return a.ctypes.data_as(dp)

@@ -1,0 +1,664 @@
+// capi.cu -- the C ABI of include/cugp.h over the CUDA path.  No CPU fallback: every compute entry point
+// needs a CUDA device and the sm_100a kernels in this library.
+#include "../../include/cugp.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <vector>
+
+#include "gp.cuh"
+#include "optim.h"
+
+namespace cugp {
+void probe_fp64_peak(float target_ms, double* dmma_tflops, double* dfma_tflops);
+void probe_gemm(int M, int N, int K, int iters, double* tflops);
+void probe_copy(size_t bytes, int iters, double* gbs);
+
+static thread_local char g_err[512] = "";
+static long g_launch_base = 0;  // launches of destroyed handles
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace cugp
+
+using namespace cugp;
+
+#define CUGP_TRY try {
+#define CUGP_CATCH                                                                                          \
+    }                                                                                                       \
+    catch (const CudaError& e) {                                                                            \
+        set_last_error("CUDA error %d (%s) at %s:%d", (int)e.code, cudaGetErrorString(e.code), e.file, e.line); \
+        cudaGetLastError();                                                                                 \
+        return e.code == cudaErrorMemoryAllocation ? CUGP_ERR_NOMEM : CUGP_ERR_CUDA;                        \
+    }                                                                                                       \
+    catch (const std::bad_alloc&) {                                                                         \
+        set_last_error("host allocation failed");                                                           \
+        return CUGP_ERR_NOMEM;                                                                              \
+    }                                                                                                       \
+    catch (...) {                                                                                           \
+        set_last_error("unexpected exception");                                                             \
+        return CUGP_ERR_CUDA;                                                                               \
+    }
+
+static int require_device() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device visible (%s): the cuGP hot path has no CPU fallback",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return CUGP_ERR_NODEVICE;
+    }
+    return CUGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct cugp_covsum {
+    int n, d;
+    std::unique_ptr<GpBatch> gp;
+    std::vector<double> Xh, yh;  // last uploaded data: lets loglik -> grad on the same (X, y) share a factorisation
+    bool have_host = false;
+};
+
+static std::vector<GpBatch*>& live_batches() {
+    static std::vector<GpBatch*> v;
+    return v;
+}
+static void track(GpBatch* g) { live_batches().push_back(g); }
+static void untrack(GpBatch* g) {
+    auto& v = live_batches();
+    g_launch_base += g->launches;
+    v.erase(std::remove(v.begin(), v.end(), g), v.end());
+}
+
+// Upload (X, y).  The host->device copy always happens (it is part of the call's cost); the factorisation
+// is kept only when the bytes are identical to the previous call's.
+static void upload(cugp_covsum* h, const double* X, const double* y) {
+    const size_t nx = (size_t)h->n * h->d, ny = (size_t)h->n;
+    const bool same = h->have_host && std::memcmp(h->Xh.data(), X, nx * 8) == 0 && std::memcmp(h->yh.data(), y, ny * 8) == 0;
+    const bool hL = h->gp->have_L, hA = h->gp->have_alpha, hT = h->gp->have_T, hK = h->gp->have_Kinv;
+    h->gp->set_data(X, y);
+    if (same) {
+        h->gp->have_L = hL; h->gp->have_alpha = hA; h->gp->have_T = hT; h->gp->have_Kinv = hK;
+    } else {
+        h->Xh.assign(X, X + nx);
+        h->yh.assign(y, y + ny);
+        h->have_host = true;
+    }
+}
+
+extern "C" {
+
+const char* cugp_version(void) { return "cugp_b200 0.1 (sm_100a)"; }
+const char* cugp_last_error(void) { return g_err; }
+
+int cugp_device_count(int* count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (count) *count = (e == cudaSuccess) ? c : 0;
+    if (e != cudaSuccess || c <= 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device visible");
+        return CUGP_ERR_NODEVICE;
+    }
+    return CUGP_OK;
+}
+int cugp_set_device(int device) {
+    CUGP_TRY
+    if (int rc = require_device()) return rc;
+    CUGP_CUDA(cudaSetDevice(device));
+    return CUGP_OK;
+    CUGP_CATCH
+}
+long cugp_launch_count(void) {
+    long s = g_launch_base;
+    for (GpBatch* g : live_batches()) s += g->launches;
+    return s;
+}
+void cugp_launch_count_reset(void) {
+    g_launch_base = 0;
+    for (GpBatch* g : live_batches()) g->launches = 0;
+}
+
+// ---- Covsum -----------------------------------------------------------------------------------------
+int cugp_covsum_create(int n, int d, cugp_covsum** out) {
+    CUGP_TRY
+    if (!out || n <= 0 || d <= 0 || d > kMaxDim) {
+        set_last_error("cugp_covsum_create: need n > 0 and 0 < d <= %d (got n=%d d=%d)", kMaxDim, n, d);
+        return CUGP_ERR_INVALID;
+    }
+    if (int rc = require_device()) return rc;
+    std::unique_ptr<cugp_covsum> h(new cugp_covsum);
+    h->n = n;
+    h->d = d;
+    h->gp.reset(new GpBatch(1, n, d));
+    track(h->gp.get());
+    *out = h.release();
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_covsum_destroy(cugp_covsum* h) {
+    if (!h) return CUGP_OK;
+    untrack(h->gp.get());
+    delete h;
+    return CUGP_OK;
+}
+int cugp_covsum_set_loghyper(cugp_covsum* h, const double theta[3]) {
+    if (!h || !theta) return CUGP_ERR_INVALID;
+    h->gp->set_theta(theta);
+    return CUGP_OK;
+}
+int cugp_covsum_get_loghyper(cugp_covsum* h, double theta[3]) {
+    if (!h || !theta) return CUGP_ERR_INVALID;
+    for (int i = 0; i < 3; i++) theta[i] = h->gp->theta[i];
+    return CUGP_OK;
+}
+int cugp_covsum_K_train(cugp_covsum* h, const double* X, double* K_out) {
+    CUGP_TRY
+    if (!h || !X || !K_out) return CUGP_ERR_INVALID;
+    GpBatch& g = *h->gp;
+    std::vector<double> y0(h->n, 0.0);
+    upload(h, X, h->have_host ? h->yh.data() : y0.data());
+    g.invalidate();  // Kb is about to hold K, not L
+    g.ensure_TW();
+    g.build_K(1);
+    launch_export_full(g.Kb, g.ld, g.n, g.Wb, g.st);
+    g.launches++;
+    CUGP_CUDA(cudaMemcpyAsync(K_out, g.Wb, (size_t)g.n * g.n * 8, cudaMemcpyDeviceToHost, g.st));
+    g.sync();
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_covsum_k_test(cugp_covsum* h, const double* X, const double* xtest, double* k_out) {
+    CUGP_TRY
+    if (!h || !X || !xtest || !k_out) return CUGP_ERR_INVALID;
+    GpBatch& g = *h->gp;
+    std::vector<double> y0(h->n, 0.0);
+    upload(h, X, h->have_host ? h->yh.data() : y0.data());
+    g.ensure_pred(64);
+    g.sync();
+    double* s = static_cast<double*>(g.stage((size_t)g.dp * 8));
+    for (int k = 0; k < g.dp; k++) s[k] = k < g.d ? xtest[k] : 0.0;
+    CUGP_CUDA(cudaMemcpyAsync(g.Xt, s, (size_t)g.dp * 8, cudaMemcpyHostToDevice, g.st));
+    // the fused mean partials are computed against `work` (any n-vector) and discarded
+    launch_cov_cross(g.Xt, 1, g.X, 0, g.n, g.dp, g.h, g.work, 0, g.Ks, g.ld, 0, g.meanpart, 0, 1, g.st);
+    g.launches++;
+    CUGP_CUDA(cudaMemcpyAsync(k_out, g.Ks, (size_t)g.n * 8, cudaMemcpyDeviceToHost, g.st));
+    g.sync();
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_covsum_loglik(cugp_covsum* h, const double* X, const double* y, double* ll) {
+    CUGP_TRY
+    if (!h || !X || !y || !ll) return CUGP_ERR_INVALID;
+    upload(h, X, y);
+    h->gp->loglik(ll);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_covsum_grad(cugp_covsum* h, const double* X, const double* y, double grad[3]) {
+    CUGP_TRY
+    if (!h || !X || !y || !grad) return CUGP_ERR_INVALID;
+    upload(h, X, y);
+    h->gp->gradient(grad);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_covsum_predict(cugp_covsum* h, const double* X, const double* y, const double* Xtest, int m, double* mean,
+                        double* var) {
+    CUGP_TRY
+    if (!h || !X || !y || m < 0 || (m > 0 && (!Xtest || !mean || !var))) return CUGP_ERR_INVALID;
+    upload(h, X, y);
+    h->gp->predict(Xtest, m, mean, var, nullptr, 0);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_nlpp(const double* actual, const double* mean, const double* var, int m, double* out) {
+    if (!actual || !mean || !var || !out || m <= 0) return CUGP_ERR_INVALID;
+    double ans = 0.0;
+    for (int i = 0; i < m; i++)
+        ans += 0.5 * std::log(6.283185 * var[i]) + std::pow(mean[i] - actual[i], 2) / (2 * var[i]);
+    *out = ans / m;
+    return CUGP_OK;
+}
+
+int cugp_covsum_set_data(cugp_covsum* h, const double* X, const double* y) {
+    CUGP_TRY
+    if (!h || !X || !y) return CUGP_ERR_INVALID;
+    upload(h, X, y);
+    h->gp->sync();
+    return CUGP_OK;
+    CUGP_CATCH
+}
+static int need_data(cugp_covsum* h) {
+    if (!h || !h->gp->have_data) {
+        set_last_error("no resident data: call cugp_covsum_set_data first");
+        return CUGP_ERR_INVALID;
+    }
+    return CUGP_OK;
+}
+int cugp_covsum_loglik_resident(cugp_covsum* h, double* ll) {
+    CUGP_TRY
+    if (int rc = need_data(h)) return rc;
+    h->gp->loglik(ll);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_covsum_grad_resident(cugp_covsum* h, double grad[3]) {
+    CUGP_TRY
+    if (int rc = need_data(h)) return rc;
+    h->gp->gradient(grad);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_covsum_scalars_resident(cugp_covsum* h, double out3[3]) {
+    CUGP_TRY
+    if (int rc = need_data(h)) return rc;
+    double s[4];
+    h->gp->scalars(s);
+    out3[0] = s[0]; out3[1] = s[1]; out3[2] = s[2];
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_covsum_alpha_resident(cugp_covsum* h, double* alpha) {
+    CUGP_TRY
+    if (int rc = need_data(h)) return rc;
+    h->gp->get_alpha(alpha);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_covsum_factorize_resident(cugp_covsum* h, float* ms_cov, float* ms_chol) {
+    CUGP_TRY
+    if (int rc = need_data(h)) return rc;
+    GpBatch& g = *h->gp;
+    g.invalidate();
+    cudaEvent_t e0, e1, e2;
+    CUGP_CUDA(cudaEventCreate(&e0));
+    CUGP_CUDA(cudaEventCreate(&e1));
+    CUGP_CUDA(cudaEventCreate(&e2));
+    CUGP_CUDA(cudaEventRecord(e0, g.st));
+    g.build_K(0);
+    CUGP_CUDA(cudaEventRecord(e1, g.st));
+    g.potrf();
+    CUGP_CUDA(cudaEventRecord(e2, g.st));
+    CUGP_CUDA(cudaEventSynchronize(e2));
+    g.have_L = true;
+    float a = 0, b = 0;
+    CUGP_CUDA(cudaEventElapsedTime(&a, e0, e1));
+    CUGP_CUDA(cudaEventElapsedTime(&b, e1, e2));
+    if (ms_cov) *ms_cov = a;
+    if (ms_chol) *ms_chol = b;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+
+static int covsum_eval(void* ctx, const double theta[3], double* f, double g[3]) {
+    cugp_covsum* h = static_cast<cugp_covsum*>(ctx);
+    try {
+        h->gp->set_theta(theta);
+        double ll;
+        h->gp->loglik(&ll);
+        h->gp->gradient(g);
+        *f = -1.0 * ll;
+        return 0;
+    } catch (const CudaError& e) {
+        set_last_error("CUDA error %d (%s) at %s:%d", (int)e.code, cudaGetErrorString(e.code), e.file, e.line);
+        return CUGP_ERR_CUDA;
+    }
+}
+int cugp_covsum_cg_solve(cugp_covsum* h, const double* X, const double* y, double* f_trace, int trace_cap, int* n_evals) {
+    CUGP_TRY
+    if (!h || !X || !y) return CUGP_ERR_INVALID;
+    upload(h, X, y);
+    double th[3] = {h->gp->theta[0], h->gp->theta[1], h->gp->theta[2]};
+    int rc = cg_minimize(covsum_eval, h, th, f_trace, trace_cap, n_evals);
+    if (rc) return rc;
+    h->gp->set_theta(th);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_covsum_rprop_solve(cugp_covsum* h, const double* X, const double* y) {
+    CUGP_TRY
+    if (!h || !X || !y) return CUGP_ERR_INVALID;
+    upload(h, X, y);
+    double th[3] = {h->gp->theta[0], h->gp->theta[1], h->gp->theta[2]};
+    int rc = rprop_minimize(covsum_eval, h, th, nullptr);
+    if (rc) return rc;
+    h->gp->set_theta(th);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+
+// Generic optimiser over a caller-supplied evaluation (multi-rank BCM: the callback allreduces).
+int cugp_cg_minimize(cugp_eval_fn fn, void* ctx, double theta[3], double* f_trace, int trace_cap, int* n_evals) {
+    if (!fn || !theta) return CUGP_ERR_INVALID;
+    return cg_minimize(fn, ctx, theta, f_trace, trace_cap, n_evals);
+}
+int cugp_rprop_minimize(cugp_eval_fn fn, void* ctx, double theta[3], int* n_iters) {
+    if (!fn || !theta) return CUGP_ERR_INVALID;
+    return rprop_minimize(fn, ctx, theta, n_iters);
+}
+
+// ---- matrixops --------------------------------------------------------------------------------------
+// A dense n x n host matrix goes into the padded device layout with one strided copy.
+static void load_matrix(GpBatch& g, const double* A) {
+    CUGP_CUDA(cudaMemcpy2DAsync(g.Kb, (size_t)g.ld * 8, A, (size_t)g.n * 8, (size_t)g.n * 8, (size_t)g.n,
+                                cudaMemcpyHostToDevice, g.st));
+    g.invalidate();
+}
+int cugp_cholesky(const double* A, double* L, int n) {
+    CUGP_TRY
+    if (!A || !L || n <= 0) return CUGP_ERR_INVALID;
+    if (int rc = require_device()) return rc;
+    GpBatch g(1, n, 1);
+    track(&g);
+    struct Untrack { GpBatch* g; ~Untrack() { untrack(g); } } u{&g};
+    load_matrix(g, A);
+    g.potrf();
+    g.ensure_TW();
+    launch_export_lower(g.Kb, g.ld, n, g.Wb, g.st);
+    g.launches++;
+    CUGP_CUDA(cudaMemcpyAsync(L, g.Wb, (size_t)n * n * 8, cudaMemcpyDeviceToHost, g.st));
+    g.sync();
+    return CUGP_OK;
+    CUGP_CATCH
+}
+static int solve_with_K(const double* K, const double* y, int n, double* quad, double* logdet, double* alpha) {
+    GpBatch g(1, n, 1);
+    track(&g);
+    struct Untrack { GpBatch* g; ~Untrack() { untrack(g); } } u{&g};
+    std::vector<double> x0(n, 0.0);
+    g.set_data(x0.data(), y);
+    load_matrix(g, K);
+    g.potrf();
+    g.have_L = true;
+    double s[4];
+    g.scalars(s);
+    if (quad) *quad = s[0];
+    if (logdet) *logdet = s[1];
+    if (alpha) g.get_alpha(alpha);
+    return CUGP_OK;
+}
+int cugp_chol_and_det(const double* K, const double* y, int n, double* quad, double* logdet) {
+    CUGP_TRY
+    if (!K || !y || n <= 0 || !quad || !logdet) return CUGP_ERR_INVALID;
+    if (int rc = require_device()) return rc;
+    return solve_with_K(K, y, n, quad, logdet, nullptr);
+    CUGP_CATCH
+}
+int cugp_kinv_y(const double* K, const double* y, double* alpha, int n) {
+    CUGP_TRY
+    if (!K || !y || !alpha || n <= 0) return CUGP_ERR_INVALID;
+    if (int rc = require_device()) return rc;
+    return solve_with_K(K, y, n, nullptr, nullptr, alpha);
+    CUGP_CATCH
+}
+int cugp_k_inverse(const double* K, double* Kinv, int n) {
+    CUGP_TRY
+    if (!K || !Kinv || n <= 0) return CUGP_ERR_INVALID;
+    if (int rc = require_device()) return rc;
+    GpBatch g(1, n, 1);
+    track(&g);
+    struct Untrack { GpBatch* g; ~Untrack() { untrack(g); } } u{&g};
+    load_matrix(g, K);
+    g.potrf();
+    g.have_L = true;
+    g.lauum();  // Wb (lower) = K^-1
+    launch_export_symmetric(g.Wb, g.ld, n, g.Tb, g.st);  // T is no longer needed: reuse as the tight output
+    g.launches++;
+    CUGP_CUDA(cudaMemcpyAsync(Kinv, g.Tb, (size_t)n * n * 8, cudaMemcpyDeviceToHost, g.st));
+    g.sync();
+    return CUGP_OK;
+    CUGP_CATCH
+}
+
+}  // extern "C"
+
+// ---- BCM --------------------------------------------------------------------------------------------
+struct cugp_bcm {
+    int N, D, K, rank, world;
+    double theta[3] = {0, 0, 0};
+    struct Group {
+        std::unique_ptr<GpBatch> gp;
+        std::vector<int> experts;  // global expert ids, ascending
+    };
+    std::vector<Group> groups;   // at most two: the floor(N/K)-row experts and the remainder expert
+    std::vector<int> local_ids;  // ascending
+    double* PQ = nullptr;        // device [2][m] scratch for the host-buffer variants
+    int pq_cap = 0;
+    cudaStream_t st = nullptr;
+    ~cugp_bcm() {
+        for (auto& g : groups) untrack(g.gp.get());
+        groups.clear();
+        if (PQ) cudaFree(PQ);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+static void bcm_moments(cugp_bcm* h, const double* Xtest, int m, double* PQ_dev) {
+    if (h->groups.empty()) {
+        CUGP_CUDA(cudaMemsetAsync(PQ_dev, 0, (size_t)2 * m * 8, h->st));
+        CUGP_CUDA(cudaStreamSynchronize(h->st));
+        return;
+    }
+    int acc = 0;
+    for (auto& g : h->groups) {
+        g.gp->predict(Xtest, m, nullptr, nullptr, PQ_dev, acc);  // all groups share h->st: ordered
+        acc = 1;
+    }
+}
+
+extern "C" {
+
+int cugp_bcm_create(const double* X, const double* y, int N, int D, int K, int rank, int world, cugp_bcm** out) {
+    CUGP_TRY
+    if (!out || !X || !y || N <= 0 || D <= 0 || D > kMaxDim || K <= 0 || K > N || world <= 0 || rank < 0 || rank >= world) {
+        set_last_error("cugp_bcm_create: bad arguments (N=%d D=%d K=%d rank=%d world=%d)", N, D, K, rank, world);
+        return CUGP_ERR_INVALID;
+    }
+    if (int rc = require_device()) return rc;
+    std::unique_ptr<cugp_bcm> h(new cugp_bcm);
+    h->N = N; h->D = D; h->K = K; h->rank = rank; h->world = world;
+    CUGP_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    const int part = N / K, last = N - (K - 1) * part;  // BCM.cpp:92-108
+    std::vector<int> uni, rem;
+    for (int e = rank; e < K; e += world) {
+        h->local_ids.push_back(e);
+        ((e == K - 1 && last != part) ? rem : uni).push_back(e);
+    }
+    auto add_group = [&](const std::vector<int>& ids, int n) {
+        if (ids.empty()) return;
+        cugp_bcm::Group g;
+        g.experts = ids;
+        g.gp.reset(new GpBatch((int)ids.size(), n, D, h->st));
+        std::vector<double> Xg((size_t)ids.size() * n * D), yg((size_t)ids.size() * n);
+        for (size_t b = 0; b < ids.size(); b++) {
+            const size_t off = (size_t)ids[b] * part;  // offset[i] = i * partition
+            std::memcpy(Xg.data() + b * n * D, X + off * D, (size_t)n * D * 8);
+            std::memcpy(yg.data() + b * n, y + off, (size_t)n * 8);
+        }
+        g.gp->set_data(Xg.data(), yg.data());
+        g.gp->sync();
+        track(g.gp.get());
+        h->groups.push_back(std::move(g));
+    };
+    add_group(uni, part);
+    add_group(rem, last);
+    *out = h.release();
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_bcm_destroy(cugp_bcm* h) {
+    delete h;
+    return CUGP_OK;
+}
+int cugp_bcm_set_loghyper(cugp_bcm* h, const double theta[3]) {
+    if (!h || !theta) return CUGP_ERR_INVALID;
+    for (int i = 0; i < 3; i++) h->theta[i] = theta[i];
+    for (auto& g : h->groups) g.gp->set_theta(theta);
+    return CUGP_OK;
+}
+int cugp_bcm_get_loghyper(cugp_bcm* h, double theta[3]) {
+    if (!h || !theta) return CUGP_ERR_INVALID;
+    for (int i = 0; i < 3; i++) theta[i] = h->theta[i];
+    return CUGP_OK;
+}
+int cugp_bcm_loglik_grad_local(cugp_bcm* h, int want_grad, double out4[4]) {
+    CUGP_TRY
+    if (!h || !out4) return CUGP_ERR_INVALID;
+    out4[0] = out4[1] = out4[2] = out4[3] = 0.0;
+    for (auto& g : h->groups) {  // groups are in ascending expert order, experts ascending inside
+        const int B = g.gp->B;
+        std::vector<double> ll(B), gr((size_t)B * 3, 0.0);
+        g.gp->loglik(ll.data());
+        if (want_grad) g.gp->gradient(gr.data());
+        for (int b = 0; b < B; b++) {
+            out4[0] += ll[b];
+            for (int k = 0; k < 3; k++) out4[1 + k] += gr[(size_t)b * 3 + k];
+        }
+    }
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_bcm_local_experts(cugp_bcm* h, int* count, int* ids, double* ll) {
+    CUGP_TRY
+    if (!h || !count) return CUGP_ERR_INVALID;
+    *count = (int)h->local_ids.size();
+    size_t k = 0;
+    for (auto& g : h->groups) {
+        std::vector<double> l(g.gp->B);
+        if (ll) g.gp->loglik(l.data());
+        for (int b = 0; b < g.gp->B; b++, k++) {
+            if (ids) ids[k] = g.experts[b];
+            if (ll) ll[k] = l[b];
+        }
+    }
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_bcm_predict_moments_dev(cugp_bcm* h, const double* Xtest, int m, double* PQ_dev) {
+    CUGP_TRY
+    if (!h || !Xtest || m <= 0 || !PQ_dev) return CUGP_ERR_INVALID;
+    bcm_moments(h, Xtest, m, PQ_dev);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+static void ensure_pq(cugp_bcm* h, int m) {
+    if (m <= h->pq_cap) return;
+    if (h->PQ) cudaFree(h->PQ);
+    h->PQ = nullptr;
+    CUGP_CUDA(cudaMalloc((void**)&h->PQ, (size_t)2 * m * 8));
+    h->pq_cap = m;
+}
+int cugp_bcm_predict_moments(cugp_bcm* h, const double* Xtest, int m, double* PQ) {
+    CUGP_TRY
+    if (!h || !Xtest || m <= 0 || !PQ) return CUGP_ERR_INVALID;
+    ensure_pq(h, m);
+    bcm_moments(h, Xtest, m, h->PQ);
+    CUGP_CUDA(cudaMemcpy(PQ, h->PQ, (size_t)2 * m * 8, cudaMemcpyDeviceToHost));
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_poe_finalize_dev(const double* PQ_dev, int m, double* mean, double* var) {
+    CUGP_TRY
+    if (!PQ_dev || m <= 0 || !mean || !var) return CUGP_ERR_INVALID;
+    double* out = nullptr;
+    CUGP_CUDA(cudaMalloc((void**)&out, (size_t)2 * m * 8));
+    launch_poe_finalize(PQ_dev, m, out, out + m, 0);
+    cudaError_t e1 = cudaMemcpy(mean, out, (size_t)m * 8, cudaMemcpyDeviceToHost);
+    cudaError_t e2 = cudaMemcpy(var, out + m, (size_t)m * 8, cudaMemcpyDeviceToHost);
+    cudaFree(out);
+    CUGP_CUDA(e1);
+    CUGP_CUDA(e2);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_poe_finalize(const double* PQ, int m, double* mean, double* var) {
+    if (!PQ || m <= 0 || !mean || !var) return CUGP_ERR_INVALID;
+    for (int t = 0; t < m; t++) {  // BCM.cpp:56-60
+        double tempvar = 1.0 / PQ[t];
+        mean[t] = tempvar * PQ[m + t];
+        var[t] = tempvar;
+    }
+    return CUGP_OK;
+}
+int cugp_bcm_predict(cugp_bcm* h, const double* Xtest, int m, double* mean, double* var) {
+    CUGP_TRY
+    if (!h || !Xtest || m <= 0 || !mean || !var) return CUGP_ERR_INVALID;
+    if (h->world != 1) {
+        set_last_error("cugp_bcm_predict needs world == 1; use predict_moments + allreduce + poe_finalize");
+        return CUGP_ERR_INVALID;
+    }
+    ensure_pq(h, m);
+    bcm_moments(h, Xtest, m, h->PQ);
+    return cugp_poe_finalize_dev(h->PQ, m, mean, var);
+    CUGP_CATCH
+}
+
+// ---- probes -----------------------------------------------------------------------------------------
+int cugp_probe_fp64_peak(float ms, double* dmma_tflops, double* dfma_tflops) {
+    CUGP_TRY
+    if (int rc = require_device()) return rc;
+    double a = 0, b = 0;
+    probe_fp64_peak(ms, &a, &b);
+    if (dmma_tflops) *dmma_tflops = a;
+    if (dfma_tflops) *dfma_tflops = b;
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_probe_gemm(int M, int N, int K, int iters, double* tflops) {
+    CUGP_TRY
+    if (int rc = require_device()) return rc;
+    if (M <= 0 || N <= 0 || K <= 0 || iters <= 0 || !tflops) return CUGP_ERR_INVALID;
+    probe_gemm(M, N, K, iters, tflops);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_debug_gemm(const double* A, const double* B, double* C, int M, int N, int K, double alpha, double beta, int a_kc,
+                    int b_kc, int flags, int config, double* colsumsq) {
+    CUGP_TRY
+    if (int rc = require_device()) return rc;
+    if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || config < 0 || config > 2) return CUGP_ERR_INVALID;
+    const int ar = a_kc ? M : K, ac = a_kc ? K : M, br = b_kc ? N : K, bc = b_kc ? K : N;
+    const int64_t lda = padded_ld(ac), ldb = padded_ld(bc), ldc = padded_ld(N);
+    const int tiles_m = cdiv(M, gemm_tile_m((GemmConfig)config));
+    double *dA = nullptr, *dB = nullptr, *dC = nullptr, *dS = nullptr;
+    CUGP_CUDA(cudaMalloc((void**)&dA, (size_t)ar * lda * 8));
+    CUGP_CUDA(cudaMalloc((void**)&dB, (size_t)br * ldb * 8));
+    CUGP_CUDA(cudaMalloc((void**)&dC, (size_t)M * ldc * 8));
+    CUGP_CUDA(cudaMalloc((void**)&dS, (size_t)tiles_m * N * 8));
+    CUGP_CUDA(cudaMemcpy2D(dA, lda * 8, A, (size_t)ac * 8, (size_t)ac * 8, ar, cudaMemcpyHostToDevice));
+    CUGP_CUDA(cudaMemcpy2D(dB, ldb * 8, B, (size_t)bc * 8, (size_t)bc * 8, br, cudaMemcpyHostToDevice));
+    CUGP_CUDA(cudaMemcpy2D(dC, ldc * 8, C, (size_t)N * 8, (size_t)N * 8, M, cudaMemcpyHostToDevice));
+    GemmParams p{};
+    p.A = dA; p.lda = lda; p.B = dB; p.ldb = ldb; p.C = dC; p.ldc = ldc;
+    p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.batch = 1;
+    p.lower_tiles = flags & 1; p.klo_ti = (flags >> 1) & 1; p.klo_tj = (flags >> 2) & 1;
+    p.khi_ti = (flags >> 3) & 1; p.khi_tj = (flags >> 4) & 1;
+    if (colsumsq) { p.colsumsq = dS; p.sCss = (int64_t)tiles_m * N; }
+    launch_gemm(p, a_kc != 0, b_kc != 0, (GemmConfig)config, 0);
+    CUGP_CUDA(cudaDeviceSynchronize());
+    CUGP_CUDA(cudaMemcpy2D(C, (size_t)N * 8, dC, ldc * 8, (size_t)N * 8, M, cudaMemcpyDeviceToHost));
+    if (colsumsq) CUGP_CUDA(cudaMemcpy(colsumsq, dS, (size_t)tiles_m * N * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dS);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_probe_copy(size_t bytes, int iters, double* gbs) {
+    CUGP_TRY
+    if (int rc = require_device()) return rc;
+    if (bytes < 16 || iters <= 0 || !gbs) return CUGP_ERR_INVALID;
+    probe_copy(bytes, iters, gbs);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,346 @@
+// gp.cu -- orchestration of the GP hot path on one GPU (see gp.cuh).
+#include "gp.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace cugp {
+
+namespace {
+template <typename T>
+void dalloc(T*& p, size_t count) {
+    if (p) return;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) throw CudaError{e, __FILE__, __LINE__};
+    p = static_cast<T*>(q);
+}
+template <typename T>
+void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// blocked factorisations built from the DMMA GEMM and the diagonal-block kernel
+// ------------------------------------------------------------------------------------------------
+void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part, int batch,
+                   cudaStream_t st, long* launches) {
+    const int nblk = cdiv(n, kDiag);
+    for (int blk = 0; blk < nblk; blk++) {
+        const int j0 = blk * kDiag;
+        launch_potrf_diag(A, ld, sA, n, j0, invd, sInvd, logdet_part, nblk, blk, batch, st);
+        if (launches) ++*launches;
+        const int m = n - (j0 + kDiag);
+        if (m <= 0) break;
+        double* A21 = A + (int64_t)(j0 + kDiag) * ld + j0;
+        // TRSM panel: L21 = A21 * inv(L11)^T, in place (each CTA owns whole rows of the panel).
+        GemmParams p{};
+        p.A = A21; p.lda = ld; p.sA = sA;
+        p.B = invd + (int64_t)blk * kDiag * kDiag; p.ldb = kDiag; p.sB = sInvd;
+        p.C = A21; p.ldc = ld; p.sC = sA;
+        p.M = m; p.N = kDiag; p.K = kDiag;
+        p.alpha = 1.0; p.beta = 0.0;
+        p.batch = batch;
+        launch_gemm(p, true, true, GEMM_TALL, st);
+        // SYRK trailing update: A22 -= L21 L21^T, lower tiles only.
+        GemmParams q{};
+        q.A = A21; q.lda = ld; q.sA = sA;
+        q.B = A21; q.ldb = ld; q.sB = sA;
+        q.C = A + (int64_t)(j0 + kDiag) * (ld + 1); q.ldc = ld; q.sC = sA;
+        q.M = m; q.N = m; q.K = kDiag;
+        q.alpha = -1.0; q.beta = 1.0;
+        q.batch = batch;
+        q.lower_tiles = 1;
+        launch_gemm(q, true, true, pick_config(m, m, batch, true), st);
+        if (launches) *launches += 2;
+    }
+}
+
+void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t sM, int n, const double* invd,
+                     int64_t sInvd, int batch, cudaStream_t st, long* launches) {
+    launch_scatter_invdiag(invd, sInvd, T, ld, sM, n, batch, st);
+    if (launches) ++*launches;
+    for (int64_t h = kDiag; h < n; h *= 2) {
+        // pairs (r1 = 2ph, r2 = r1 + h): T21 = -T22 (L21 T11).  `full` pairs have an h x h lower-right block.
+        const int full = (int)(n / (2 * h));
+        const int64_t pair_stride = 2 * h * (ld + 1);
+        for (int pass = 0; pass < 2; pass++) {
+            int npairs, n2;
+            int64_t base;
+            if (pass == 0) {
+                npairs = full; n2 = (int)h; base = 0;
+            } else {
+                const int64_t r2 = (int64_t)full * 2 * h + h;
+                if (r2 >= n) break;
+                npairs = 1; n2 = (int)(n - r2); base = (int64_t)full * pair_stride;
+            }
+            if (npairs == 0) continue;
+            const int64_t o21 = base + h * ld;        // block (2,1): rows r2.., cols r1..
+            const int64_t o11 = base;                 // block (1,1)
+            const int64_t o22 = base + h * (ld + 1);  // block (2,2)
+            const int tot = npairs * batch;
+            GemmParams p{};  // tmp = L21 * T11   (T11 lower: k >= column tile start)
+            p.A = L + o21; p.lda = ld;
+            p.B = T + o11; p.ldb = ld;
+            p.C = W + o21; p.ldc = ld;
+            p.M = n2; p.N = (int)h; p.K = (int)h;
+            p.alpha = 1.0; p.beta = 0.0;
+            p.batch = tot; p.batch_inner = npairs;
+            p.sA = p.sB = p.sC = pair_stride;
+            p.sA2 = p.sB2 = p.sC2 = sM;
+            p.klo_tj = 1;
+            if (npairs == 1) { p.batch_inner = 0; p.sA = p.sB = p.sC = sM; }
+            GemmConfig cfg = pick_config(n2, (int)h, tot, false);
+            launch_gemm(p, true, false, cfg, st);
+            GemmParams q{};  // T21 = -T22 * tmp   (T22 lower: k < row tile end)
+            q.A = T + o22; q.lda = ld;
+            q.B = W + o21; q.ldb = ld;
+            q.C = T + o21; q.ldc = ld;
+            q.M = n2; q.N = (int)h; q.K = n2;
+            q.alpha = -1.0; q.beta = 0.0;
+            q.batch = tot; q.batch_inner = npairs;
+            q.sA = q.sB = q.sC = pair_stride;
+            q.sA2 = q.sB2 = q.sC2 = sM;
+            q.khi_ti = 1;
+            if (npairs == 1) { q.batch_inner = 0; q.sA = q.sB = q.sC = sM; }
+            launch_gemm(q, true, false, cfg, st);
+            if (launches) *launches += 2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GpBatch
+// ------------------------------------------------------------------------------------------------
+GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(d_) {
+    dp = (int)round_up(d, 2);
+    h = make_hyper(theta);
+    ld = padded_ld(n);
+    nblk = cdiv(n, kDiag);
+    if (stream) {
+        st = stream;
+    } else {
+        CUGP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        own_stream = true;
+    }
+    const size_t bn = (size_t)B * n;
+    dalloc(X, bn * dp);
+    dalloc(y, bn);
+    dalloc(Kb, (size_t)B * n * ld);
+    dalloc(invd, (size_t)B * nblk * kDiag * kDiag);
+    dalloc(logdet_part, (size_t)B * nblk);
+    dalloc(work, bn);
+    dalloc(z, bn);
+    dalloc(alpha, bn);
+    dalloc(scal, (size_t)B * 4);
+    dalloc(gradout, (size_t)B * 3);
+}
+
+GpBatch::~GpBatch() {
+    if (st) cudaStreamSynchronize(st);
+    dfree(X); dfree(y); dfree(Kb); dfree(invd); dfree(logdet_part); dfree(work); dfree(z); dfree(alpha); dfree(scal);
+    dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout);
+    dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar);
+    if (hstage) cudaFreeHost(hstage);
+    if (own_stream && st) cudaStreamDestroy(st);
+}
+
+void* GpBatch::stage(size_t bytes) {
+    if (bytes > hstage_bytes) {
+        if (hstage) {
+            CUGP_CUDA(cudaStreamSynchronize(st));
+            cudaFreeHost(hstage);
+            hstage = nullptr;
+        }
+        CUGP_CUDA(cudaMallocHost((void**)&hstage, bytes));
+        hstage_bytes = bytes;
+    }
+    return hstage;
+}
+
+void GpBatch::set_data(const double* Xh, const double* yh) {
+    const size_t rows = (size_t)B * n;
+    CUGP_CUDA(cudaStreamSynchronize(st));  // staging buffer may still feed an earlier copy
+    double* s = static_cast<double*>(stage((rows * dp + rows) * sizeof(double)));
+    if (dp == d) {
+        std::memcpy(s, Xh, rows * d * sizeof(double));
+    } else {
+        for (size_t r = 0; r < rows; r++) {
+            std::memcpy(s + r * dp, Xh + r * d, d * sizeof(double));
+            for (int k = d; k < dp; k++) s[r * dp + k] = 0.0;  // a zero extra coordinate adds exactly +0 to |xi-xj|^2
+        }
+    }
+    std::memcpy(s + rows * dp, yh, rows * sizeof(double));
+    CUGP_CUDA(cudaMemcpyAsync(X, s, rows * dp * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUGP_CUDA(cudaMemcpyAsync(y, s + rows * dp, rows * sizeof(double), cudaMemcpyHostToDevice, st));
+    have_data = true;
+    invalidate();
+}
+
+void GpBatch::set_theta(const double th[3]) {
+    if (th[0] == theta[0] && th[1] == theta[1] && th[2] == theta[2] && have_L) return;  // cached factor stays valid
+    theta[0] = th[0]; theta[1] = th[1]; theta[2] = th[2];
+    h = make_hyper(theta);
+    invalidate();
+}
+
+void GpBatch::build_K(int full) {
+    launch_cov_train(X, (int64_t)n * dp, n, dp, h, Kb, ld, mat_stride(), B, full, st);
+    launches++;
+}
+
+void GpBatch::potrf() {
+    potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches);
+}
+
+void GpBatch::factorize() {
+    if (have_L) return;
+    build_K(0);
+    potrf();
+    have_L = true;
+}
+
+void GpBatch::solve() {
+    if (have_alpha) return;
+    factorize();
+    const int64_t sI = (int64_t)nblk * kDiag * kDiag;
+    launch_copy_vec(y, work, (int64_t)B * n, st);
+    launch_trsv_forward(Kb, ld, mat_stride(), n, invd, sI, work, z, n, B, st);
+    launch_trsv_backward(Kb, ld, mat_stride(), n, invd, sI, z, alpha, n, B, st);  // z doubles as the work vector
+    launch_ll_finalize(y, alpha, n, n, logdet_part, nblk, scal, B, st);
+    launches += 2 + 2 * nblk;
+    have_alpha = true;
+}
+
+void GpBatch::ensure_TW() {
+    dalloc(Tb, (size_t)B * n * ld);
+    dalloc(Wb, (size_t)B * n * ld);
+}
+
+void GpBatch::trtri() {
+    if (have_T) return;
+    factorize();
+    ensure_TW();
+    trtri_recursive(Kb, Tb, Wb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, B, st, &launches);
+    have_T = true;
+    have_Kinv = false;
+}
+
+void GpBatch::lauum() {
+    if (have_Kinv) return;
+    trtri();
+    GemmParams p{};  // Kinv = T^T T: k >= max(i,j) = row-tile start on the lower tile set
+    p.A = Tb; p.lda = ld; p.sA = mat_stride();
+    p.B = Tb; p.ldb = ld; p.sB = mat_stride();
+    p.C = Wb; p.ldc = ld; p.sC = mat_stride();
+    p.M = n; p.N = n; p.K = n;
+    p.alpha = 1.0; p.beta = 0.0;
+    p.batch = B;
+    p.lower_tiles = 1;
+    p.klo_ti = 1;
+    launch_gemm(p, false, false, pick_config(n, n, B, true), st);
+    launches++;
+    have_Kinv = true;
+}
+
+void GpBatch::scalars(double* out4) {
+    solve();
+    CUGP_CUDA(cudaMemcpyAsync(out4, scal, (size_t)B * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    sync();
+}
+
+void GpBatch::loglik(double* ll_out) {
+    std::vector<double> s((size_t)B * 4);
+    scalars(s.data());
+    for (int b = 0; b < B; b++) ll_out[b] = s[(size_t)b * 4 + 2];
+}
+
+void GpBatch::gradient(double* g_out) {
+    solve();
+    lauum();
+    dalloc(gradpart, grad_trace_partials(n, B));
+    launch_grad_trace(X, (int64_t)n * dp, n, dp, h, Wb, ld, mat_stride(), alpha, n, gradpart, gradout, B, st);
+    launches += 2;
+    CUGP_CUDA(cudaMemcpyAsync(g_out, gradout, (size_t)B * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    sync();
+}
+
+void GpBatch::get_alpha(double* out) {
+    solve();
+    CUGP_CUDA(cudaMemcpyAsync(out, alpha, (size_t)B * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    sync();
+}
+
+void GpBatch::ensure_pred(int mc) {
+    if (mc <= pred_cap) return;
+    sync();
+    dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar);
+    const size_t tiles64 = (size_t)cdiv(n, 64);
+    dalloc(Xt, (size_t)mc * dp);
+    dalloc(Ks, (size_t)B * mc * ld);
+    dalloc(meanpart, (size_t)B * tiles64 * mc);
+    dalloc(css, (size_t)B * tiles64 * mc);
+    dalloc(pmean, (size_t)B * mc);
+    dalloc(pvar, (size_t)B * mc);
+    pred_cap = mc;
+}
+
+// Predictive moments of every GP in the batch at m test points (covkernel.cpp:277-306):
+//   mean = k*' alpha ;  var = sf2 + sn2 - |L^-1 k*|^2  ( = sf2 + sn2 - k*' K^-1 k* ).
+// mean_h/var_h: [B][m] host (may be null).  PQ_dev: [2][m] device product-of-experts moments (may be null).
+void GpBatch::predict(const double* Xt_h, int m, double* mean_h, double* var_h, double* PQ_dev, int accumulate) {
+    if (m <= 0) return;
+    solve();
+    trtri();
+    // chunk the test set so Kstar stays near 2 GB
+    int64_t cap = (int64_t)(2.0e9 / ((double)B * ld * 8.0));
+    int mc = (int)std::min<int64_t>(m, std::max<int64_t>(64, cap / 64 * 64));
+    ensure_pred(mc);
+    const int tiles_j = cdiv(n, kCovTile);
+    for (int t0 = 0; t0 < m; t0 += mc) {
+        const int cur = std::min(mc, m - t0);
+        sync();
+        double* s = static_cast<double*>(stage((size_t)cur * dp * sizeof(double)));
+        for (int r = 0; r < cur; r++) {
+            std::memcpy(s + (size_t)r * dp, Xt_h + (size_t)(t0 + r) * d, d * sizeof(double));
+            for (int k = d; k < dp; k++) s[(size_t)r * dp + k] = 0.0;
+        }
+        CUGP_CUDA(cudaMemcpyAsync(Xt, s, (size_t)cur * dp * sizeof(double), cudaMemcpyHostToDevice, st));
+        launch_cov_cross(Xt, cur, X, (int64_t)n * dp, n, dp, h, alpha, n, Ks, ld, (int64_t)mc * ld, meanpart,
+                         (int64_t)tiles_j * mc, B, st);
+        GemmParams p{};  // V = T Kstar^T ; only the column sums of squares are kept
+        p.A = Tb; p.lda = ld; p.sA = mat_stride();
+        p.B = Ks; p.ldb = ld; p.sB = (int64_t)mc * ld;
+        p.M = n; p.N = cur; p.K = n;
+        p.alpha = 1.0; p.beta = 0.0;
+        p.batch = B;
+        p.khi_ti = 1;
+        p.colsumsq = css;
+        const GemmConfig cfg = pick_config(n, cur, B, false);
+        const int tiles_m = cdiv(n, gemm_tile_m(cfg));
+        p.sCss = (int64_t)tiles_m * cur;
+        launch_gemm(p, true, true, cfg, st);
+        // meanpart was written with row length `cur` (ni) and batch stride tiles_j*mc
+        launch_predict_finalize(meanpart, tiles_j, css, tiles_m, cur, h, pmean, pvar, mc, (int64_t)tiles_j * mc, p.sCss,
+                                B, st);
+        launches += 3;
+        if (PQ_dev) {
+            launch_poe_accumulate(pmean, pvar, mc, B, cur, PQ_dev + t0, PQ_dev + m + t0, accumulate, st);
+            launches++;
+        }
+        if (mean_h && var_h) {
+            for (int b = 0; b < B; b++) {
+                CUGP_CUDA(cudaMemcpyAsync(mean_h + (size_t)b * m + t0, pmean + (size_t)b * mc, cur * sizeof(double),
+                                          cudaMemcpyDeviceToHost, st));
+                CUGP_CUDA(cudaMemcpyAsync(var_h + (size_t)b * m + t0, pvar + (size_t)b * mc, cur * sizeof(double),
+                                          cudaMemcpyDeviceToHost, st));
+            }
+        }
+    }
+    sync();
+}
+
+}  // namespace cugp

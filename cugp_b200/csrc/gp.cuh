@@ -1,0 +1,76 @@
+// gp.cuh -- device-resident state and orchestration of a batch of independent exact GPs of one size.
+// B = 1 is the reference's `Covsum` (cpp_serial_gp/covkernel.h:3-38); B > 1 is the set of equally sized
+// BCM experts one GPU owns (distributed_gp/BCM.cpp:85-110), processed together so every launch carries
+// all of them.
+#pragma once
+#include "common.cuh"
+#include "gemm_dmma.cuh"
+#include "kernels.cuh"
+
+namespace cugp {
+
+struct GpBatch {
+    int B = 0, n = 0, d = 0, dp = 0, nblk = 0;
+    int64_t ld = 0;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+
+    // device buffers
+    double *X = nullptr, *y = nullptr;      // [B][n][dp], [B][n]
+    double* Kb = nullptr;                   // [B][n][ld]: K, then L in place
+    double* invd = nullptr;                 // [B][nblk][128][128] inverses of L's diagonal blocks
+    double* logdet_part = nullptr;          // [B][nblk]
+    double *work = nullptr, *z = nullptr, *alpha = nullptr;  // [B][n]
+    double* scal = nullptr;                 // [B][4] quad, logdet, LL
+    double *Tb = nullptr, *Wb = nullptr;    // [B][n][ld] lazily: T = L^-1 ; scratch, then Kinv (lower)
+    double *gradpart = nullptr, *gradout = nullptr;
+    // prediction workspace (lazily sized)
+    double *Xt = nullptr, *Ks = nullptr, *meanpart = nullptr, *css = nullptr, *pmean = nullptr, *pvar = nullptr;
+    int pred_cap = 0;
+    // pinned host staging
+    double* hstage = nullptr;
+    size_t hstage_bytes = 0;
+
+    double theta[3] = {0, 0, 0};
+    Hyper h{};
+    bool have_data = false, have_L = false, have_alpha = false, have_T = false, have_Kinv = false;
+    long launches = 0;  // kernels launched since the last reset (bench.py `gpu_launches`)
+
+    GpBatch(int B, int n, int d, cudaStream_t stream = nullptr);
+    ~GpBatch();
+    GpBatch(const GpBatch&) = delete;
+    GpBatch& operator=(const GpBatch&) = delete;
+
+    // X: B*n rows of d doubles (host, tight), y: B*n.  Packs to the padded device layout.
+    void set_data(const double* Xh, const double* yh);
+    void set_theta(const double th[3]);
+    void invalidate() { have_L = have_alpha = have_T = have_Kinv = false; }
+
+    void build_K(int full);                 // K1 into Kb
+    void potrf();                           // K2 on Kb (expects K in the lower triangle)
+    void factorize();                       // build_K + potrf (cached)
+    void solve();                           // + K3: alpha, quad, logdet, LL (cached)
+    void trtri();                           // T = L^-1 (cached)
+    void lauum();                           // Kinv (lower) = T^T T into Wb (cached)
+    void loglik(double* ll_out);            // [B] host
+    void scalars(double* out4);             // [B][4] host: quad, logdet, LL, 0
+    void gradient(double* g_out);           // [B][3] host, d(-LL)/dtheta
+    void predict(const double* Xt_h, int m, double* mean_h, double* var_h, double* PQ_dev, int accumulate);
+    void get_alpha(double* out);            // [B][n] host
+
+    void sync() { CUGP_CUDA(cudaStreamSynchronize(st)); }
+    void* stage(size_t bytes);
+    int64_t mat_stride() const { return (int64_t)n * ld; }
+    void ensure_TW();
+    void ensure_pred(int mc);
+};
+
+// Blocked right-looking Cholesky of `batch` matrices in place (lower), with the inverses of the
+// 128x128 diagonal blocks and per-block log-determinant partials as by-products.
+void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part,
+                   int batch, cudaStream_t st, long* launches);
+// T = L^-1 by recursive doubling over 128-blocks (W is n x n scratch).
+void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t sM, int n, const double* invd,
+                     int64_t sInvd, int batch, cudaStream_t st, long* launches);
+
+}  // namespace cugp

@@ -1,0 +1,737 @@
+// kernels.cu -- hand-written sm_100a kernels of the GP hot path other than the DMMA GEMM:
+//   K1  covariance build (TMA bulk staging of X tiles, strict reference arithmetic order)
+//   K5a cross covariance fused with the predictive-mean partials
+//   K4  fused gradient trace (K and D rebuilt on the fly, Kinv streamed once)
+//   K2a 128x128 diagonal-block Cholesky + triangular inverse (one CTA, shared memory)
+//   K3  blocked triangular solves (forward / backward), log-likelihood finalisation
+// Every reduction is a fixed-shape tree over per-CTA partials: results are run-to-run deterministic.
+#include "kernels.cuh"
+
+namespace cugp {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// TMA (1-D bulk async copy) + mbarrier primitives.  SASS: UBLKCP / SYNCS.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+                 "l"(gsrc), "r"(bytes), "r"(a)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(a),
+        "r"(parity)
+        : "memory");
+}
+
+// (ti, tj) with ti >= tj from a linear index over the lower-triangular tile set.
+__device__ __forceinline__ void lower_tile(int x, int& ti, int& tj) {
+    ti = (int)((sqrt(8.0 * (double)x + 1.0) - 1.0) * 0.5);
+    while ((int64_t)(ti + 1) * (ti + 2) / 2 <= x) ti++;
+    while ((int64_t)ti * (ti + 1) / 2 > x) ti--;
+    tj = x - (int)((int64_t)ti * (ti + 1) / 2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Covariance tiles.  64x64 outputs per CTA, 256 threads, each thread a 4x4 micro-tile:
+//   rows  i0 + ty*4 + a            (a < 4)
+//   cols  j0 + tx*2 + 32*b + e     (b < 2, e < 2)  -> 16-byte vector stores, 256 B contiguous per half-warp
+// ------------------------------------------------------------------------------------------------
+constexpr int CT = kCovTile;
+constexpr int COV_THREADS = 256;
+enum CovMode { COV_LOWER = 0, COV_FULL = 1, COV_CROSS = 2, COV_TRACE = 3 };
+
+struct CovArgs {
+    const double* Xi; int64_t sXi; int ni;
+    const double* Xj; int64_t sXj; int nj;
+    int dp;
+    Hyper h;
+    double* out; int64_t ld, sOut;
+    const double* alpha; int64_t sAlpha;
+    double* part; int64_t sPart;
+    const double* Kinv; int64_t sKinv;
+    int tiles_j;
+};
+
+// Stage the two X tiles: TMA bulk copy of the contiguous row blocks, then an in-smem transpose to
+// [k][row] so the micro-tile operand loads are 16-byte, conflict-free and broadcast friendly.
+__device__ __forceinline__ void stage_x_tiles(double* smem, const double* Xi, int i0, int ni, const double* Xj, int j0,
+                                              int nj, int dp, unsigned long long* bar, double*& xt_i, double*& xt_j) {
+    const int tid = threadIdx.x;
+    double* raw_i = smem;
+    double* raw_j = smem + CT * dp;
+    xt_i = smem + 2 * CT * dp;
+    xt_j = smem + 3 * CT * dp;
+    const int rows_i = min(CT, ni - i0), rows_j = min(CT, nj - j0);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned bi = (unsigned)(rows_i * dp * 8), bj = (unsigned)(rows_j * dp * 8);
+        mbar_expect_tx(bar, bi + bj);
+        bulk_g2s(raw_i, Xi + (int64_t)i0 * dp, bi, bar);
+        bulk_g2s(raw_j, Xj + (int64_t)j0 * dp, bj, bar);
+    }
+    mbar_wait(bar, 0);
+    for (int e = tid; e < CT * dp; e += COV_THREADS) {
+        int r = e % CT, k = e / CT;
+        xt_i[k * CT + r] = r < rows_i ? raw_i[r * dp + k] : 0.0;
+        xt_j[k * CT + r] = r < rows_j ? raw_j[r * dp + k] : 0.0;
+    }
+    __syncthreads();
+}
+
+// Squared distances of the 4x4 micro-tile, accumulated in dimension order with separately rounded
+// subtract / multiply / add -- the reference's subtract_vec + dotproduct_vec (matrixops.cpp:216-229)
+// compiled without FMA contraction -- so d2 is bit-identical to the CPU path.
+__device__ __forceinline__ void micro_d2(const double* xt_i, const double* xt_j, int dp, int ty, int tx,
+                                         double d2[4][4]) {
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) d2[a][c] = 0.0;
+    for (int k = 0; k < dp; k++) {
+        const double2 ia = *reinterpret_cast<const double2*>(xt_i + k * CT + ty * 4);
+        const double2 ib = *reinterpret_cast<const double2*>(xt_i + k * CT + ty * 4 + 2);
+        const double2 ja = *reinterpret_cast<const double2*>(xt_j + k * CT + tx * 2);
+        const double2 jb = *reinterpret_cast<const double2*>(xt_j + k * CT + tx * 2 + 32);
+        const double xi[4] = {ia.x, ia.y, ib.x, ib.y};
+        const double xj[4] = {ja.x, ja.y, jb.x, jb.y};
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double t = __dsub_rn(xi[a], xj[c]);
+                d2[a][c] = __dadd_rn(d2[a][c], __dmul_rn(t, t));
+            }
+    }
+}
+
+// sf2 * exp(-d2 * 0.5 / ell_sq): same operation order as covkernel.cpp:89 (division kept as a division).
+__device__ __forceinline__ double se_kernel(double d2, const Hyper& h) {
+    return h.sf2 * exp(__ddiv_rn(__dmul_rn(-d2, 0.5), h.ell_sq));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ double red[3 * (COV_THREADS / 32)];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t b = blockIdx.y;
+    int ti, tj;
+    if (MODE == COV_CROSS) {
+        ti = blockIdx.x / p.tiles_j;
+        tj = blockIdx.x % p.tiles_j;
+    } else {
+        lower_tile(blockIdx.x, ti, tj);
+    }
+    const int i0 = ti * CT, j0 = tj * CT;
+    const double* Xi = p.Xi + b * p.sXi;
+    const double* Xj = p.Xj + b * p.sXj;
+    double *xt_i, *xt_j;
+    stage_x_tiles(smem, Xi, i0, p.ni, Xj, j0, p.nj, p.dp, &bar, xt_i, xt_j);
+
+    double d2[4][4];
+    micro_d2(xt_i, xt_j, p.dp, ty, tx, d2);
+
+    if (MODE == COV_LOWER || MODE == COV_FULL) {
+        double* K = p.out + b * p.sOut;
+        double v[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            int gi = i0 + ty * 4 + a;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int gj = j0 + tx * 2 + 32 * (c >> 1) + (c & 1);
+                double val = se_kernel(d2[a][c], p.h);
+                if (gi == gj) val += p.h.sn2;  // covkernel.cpp:93-94
+                v[a][c] = val;
+            }
+            if (gi < p.ni) {
+#pragma unroll
+                for (int bb = 0; bb < 2; bb++) {
+                    int gj = j0 + tx * 2 + 32 * bb;
+                    double* dst = K + (int64_t)gi * p.ld + gj;
+                    if (gj + 1 < p.nj) *reinterpret_cast<double2*>(dst) = make_double2(v[a][2 * bb], v[a][2 * bb + 1]);
+                    else if (gj < p.nj) dst[0] = v[a][2 * bb];
+                }
+            }
+        }
+        if (MODE == COV_FULL && ti > tj) {  // mirror: covkernel.cpp:90-91 fills both triangles
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int gj = j0 + tx * 2 + 32 * (c >> 1) + (c & 1);
+                if (gj >= p.nj) continue;
+                int gi = i0 + ty * 4;
+                double* dst = K + (int64_t)gj * p.ld + gi;
+                if (gi + 3 < p.ni) {
+                    *reinterpret_cast<double2*>(dst) = make_double2(v[0][c], v[1][c]);
+                    *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2][c], v[3][c]);
+                } else {
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+                        if (gi + a < p.ni) dst[a] = v[a][c];
+                }
+            }
+        }
+    } else if (MODE == COV_CROSS) {
+        double* Ks = p.out + b * p.sOut;
+        const double* alpha = p.alpha + b * p.sAlpha;
+        double al[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int gj = j0 + tx * 2 + 32 * (c >> 1) + (c & 1);
+            al[c] = gj < p.nj ? alpha[gj] : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            int gi = i0 + ty * 4 + a;
+            double v[4], s = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                v[c] = se_kernel(d2[a][c], p.h);
+                s += v[c] * al[c];
+            }
+            if (gi < p.ni) {
+#pragma unroll
+                for (int bb = 0; bb < 2; bb++) {
+                    int gj = j0 + tx * 2 + 32 * bb;
+                    double* dst = Ks + (int64_t)gi * p.ld + gj;
+                    if (gj + 1 < p.nj) *reinterpret_cast<double2*>(dst) = make_double2(v[2 * bb], v[2 * bb + 1]);
+                    else if (gj < p.nj) dst[0] = v[2 * bb];
+                }
+            }
+#pragma unroll
+            for (int off = 1; off < 16; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (tx == 0 && gi < p.ni) p.part[b * p.sPart + (int64_t)tj * p.ni + gi] = s;
+        }
+    } else {  // COV_TRACE
+        const double* Kinv = p.Kinv + b * p.sKinv;
+        const double* alpha = p.alpha + b * p.sAlpha;
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        double aj[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int gj = j0 + tx * 2 + 32 * (c >> 1) + (c & 1);
+            aj[c] = gj < p.nj ? alpha[gj] : 0.0;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            int gi = i0 + ty * 4 + a;
+            if (gi >= p.ni) continue;
+            double ai = alpha[gi];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int gj = j0 + tx * 2 + 32 * (c >> 1) + (c & 1);
+                if (gj > gi || gj >= p.nj) continue;
+                double w = Kinv[(int64_t)gi * p.ld + gj] - ai * aj[c];  // W = Kinv - alpha alpha^T (covkernel.cpp:221)
+                if (gi == gj) {
+                    s2 += w * p.h.sf2;  // K_ii - sn2 = sf2 * exp(0)
+                    s3 += w;
+                } else {
+                    double kv = se_kernel(d2[a][c], p.h);
+                    s1 += 2.0 * (w * (kv * (d2[a][c] / p.h.ell_sq)));  // covkernel.cpp:148,186,247
+                    s2 += 2.0 * (w * kv);
+                }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, off);
+        }
+        const int warp = tid >> 5, lane = tid & 31;
+        if (lane == 0) {
+            red[warp] = s1;
+            red[8 + warp] = s2;
+            red[16 + warp] = s3;
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double s = 0.0;
+            for (int w = 0; w < COV_THREADS / 32; w++) s += red[tid * 8 + w];
+            p.part[b * p.sPart + (int64_t)blockIdx.x * 3 + tid] = s;
+        }
+    }
+}
+
+// Fixed-order reduction of the per-tile trace partials -> gradient of the NEGATIVE log-likelihood.
+__global__ void __launch_bounds__(256) grad_reduce_kernel(const double* part, int64_t sPart, int ntiles, Hyper h,
+                                                          double* out) {
+    __shared__ double red[3][256];
+    const int64_t b = blockIdx.x;
+    const double* pp = part + b * sPart;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int t = threadIdx.x; t < ntiles; t += 256)
+        for (int c = 0; c < 3; c++) s[c] += pp[(int64_t)t * 3 + c];
+    for (int c = 0; c < 3; c++) red[c][threadIdx.x] = s[c];
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off)
+            for (int c = 0; c < 3; c++) red[c][threadIdx.x] += red[c][threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[b * 3 + 0] = red[0][0] / 2.0;        // psum1/2 (covkernel.cpp:259)
+        out[b * 3 + 1] = red[1][0];              // psum2/2 = sum W.*(K - sn2 I)
+        out[b * 3 + 2] = h.sn2 * red[2][0];      // psum3/2 = sn2 * tr W
+    }
+}
+
+template <int MODE>
+void launch_cov(const CovArgs& a, int64_t tiles, int batch, cudaStream_t st) {
+    size_t smem = (size_t)4 * CT * a.dp * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUGP_CUDA(cudaFuncSetAttribute(cov_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    if (tiles <= 0 || batch <= 0) return;
+    cov_tile_kernel<MODE><<<dim3((unsigned)tiles, (unsigned)batch), COV_THREADS, smem, st>>>(a);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a: Cholesky + triangular inverse of a 128x128 diagonal block in shared memory.
+// S is 128 x 129: the lower triangle holds A -> L; the inverse is built in the strictly upper part,
+// R(i,j) = S[j][i+1] for i >= j, so one 132 KB array serves both (odd row stride: column walks are
+// conflict-free).
+// ------------------------------------------------------------------------------------------------
+constexpr int DB = kDiag;
+constexpr int DLD = DB + 1;
+constexpr int DIAG_THREADS = 512;
+
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
+    potrf_diag_kernel(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd,
+                      double* logdet_part, int nblk, int blk) {
+    extern __shared__ __align__(16) double S[];
+    __shared__ double red[DB];
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;  // 32 x 16
+    const int64_t b = blockIdx.x;
+    double* Ab = A + b * sA + (int64_t)j0 * ld + j0;
+    const int nb = min(DB, n - j0);
+
+    for (int e = tid; e < DB * DLD; e += DIAG_THREADS) {
+        int i = e / DLD, j = e % DLD;
+        double v = 0.0;
+        if (j <= i) {  // lower triangle of A, identity padded
+            if (i < nb) v = Ab[(int64_t)i * ld + j];
+            else if (i == j) v = 1.0;
+        } else if (j == i + 1) {
+            v = 1.0;  // R = I
+        }
+        S[e] = v;
+    }
+    __syncthreads();
+
+    // Right-looking Cholesky, one column per step (matrixops.cpp:74-98 restricted to the block).
+    for (int k = 0; k < DB; k++) {
+        const double dk = sqrt(S[k * DLD + k]);  // negative pivot -> NaN, propagates (matrixops.cpp:77)
+        for (int i = k + 1 + tid; i < DB; i += DIAG_THREADS) S[i * DLD + k] = S[i * DLD + k] / dk;
+        __syncthreads();
+        if (tid == 0) S[k * DLD + k] = dk;
+        for (int i = k + 1 + ty; i < DB; i += 16) {
+            const double lik = S[i * DLD + k];
+            for (int j = k + 1 + tx; j <= i; j += 32) S[i * DLD + j] -= lik * S[j * DLD + k];
+        }
+        __syncthreads();
+    }
+
+    // Inverse by forward substitution against I, all columns at once (matrixops.cpp:330-340).
+    for (int k = 0; k < DB; k++) {
+        const double dk = S[k * DLD + k];
+        for (int j = tid; j <= k; j += DIAG_THREADS) S[j * DLD + k + 1] = S[j * DLD + k + 1] / dk;  // T[k][j]
+        __syncthreads();
+        for (int j = ty; j <= k; j += 16) {
+            const double tkj = S[j * DLD + k + 1];
+            for (int i = k + 1 + tx; i < DB; i += 32) S[j * DLD + i + 1] -= S[i * DLD + k] * tkj;
+        }
+        __syncthreads();
+    }
+
+    // write back: L11 with zeroed upper triangle, inv(L11) dense 128x128 (zero upper)
+    double* inv = invd + b * sInvd;
+    for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
+        int i = e / DB, j = e % DB;
+        if (i < nb && j < nb) Ab[(int64_t)i * ld + j] = (j <= i) ? S[i * DLD + j] : 0.0;
+        inv[e] = (j <= i) ? S[j * DLD + i + 1] : 0.0;
+    }
+    if (tid < DB) red[tid] = log(S[tid * DLD + tid]);
+    __syncthreads();
+    for (int off = DB / 2; off > 0; off >>= 1) {
+        if (tid < off) red[tid] += red[tid + off];
+        __syncthreads();
+    }
+    if (tid == 0) logdet_part[b * nblk + blk] = red[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: triangular solves.  One launch per 128-column block; every CTA first recomputes the block's
+// solution with the stored inverse of the diagonal block (128x128 GEMV, L2 resident) and then applies
+// it to its own slice of the remaining right-hand side, so a sweep streams L exactly once.
+// ------------------------------------------------------------------------------------------------
+constexpr int TRSV_THREADS = 256;
+constexpr int FWD_ROWS = 256;   // rows of the panel below handled per CTA
+constexpr int BWD_COLS = 512;   // columns of the block row handled per CTA
+
+__global__ void __launch_bounds__(TRSV_THREADS)
+    trsv_fwd_step_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int n, int j0,
+                         const double* __restrict__ invd, int64_t sInvd, double* work, double* z, int64_t sVec) {
+    __shared__ __align__(16) double rj[DB];
+    __shared__ __align__(16) double zj[DB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b = blockIdx.y;
+    L += b * sL;
+    invd += b * sInvd + (int64_t)(j0 / DB) * DB * DB;
+    work += b * sVec;
+    z += b * sVec;
+    const int nb = min(DB, n - j0);
+    if (tid < DB) rj[tid] = tid < nb ? work[j0 + tid] : 0.0;
+    __syncthreads();
+    // z_j = inv(L_jj) r_j
+    {
+        const double2 r0 = *reinterpret_cast<const double2*>(rj + lane * 4);
+        const double2 r1 = *reinterpret_cast<const double2*>(rj + lane * 4 + 2);
+#pragma unroll 4
+        for (int rr = 0; rr < DB / 8; rr++) {
+            int row = warp * (DB / 8) + rr;
+            const double2 a0 = *reinterpret_cast<const double2*>(invd + row * DB + lane * 4);
+            const double2 a1 = *reinterpret_cast<const double2*>(invd + row * DB + lane * 4 + 2);
+            double s = a0.x * r0.x + a0.y * r0.y + a1.x * r1.x + a1.y * r1.y;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) zj[row] = s;
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid < nb) z[j0 + tid] = zj[tid];
+    // r_i -= L[i, j-block] z_j for this CTA's rows below the block
+    const int row_base = j0 + DB + blockIdx.x * FWD_ROWS;
+    const double2 z0 = *reinterpret_cast<const double2*>(zj + lane * 4);
+    const double2 z1 = *reinterpret_cast<const double2*>(zj + lane * 4 + 2);
+    constexpr int RPW = FWD_ROWS / (TRSV_THREADS / 32);  // rows per warp
+    for (int r4 = 0; r4 < RPW; r4 += 4) {
+        double s[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int i = row_base + warp * RPW + r4 + u;
+            s[u] = 0.0;
+            if (i < n) {
+                const double* src = L + (int64_t)i * ld + j0 + lane * 4;
+                const double2 a0 = *reinterpret_cast<const double2*>(src);
+                const double2 a1 = *reinterpret_cast<const double2*>(src + 2);
+                s[u] = a0.x * z0.x + a0.y * z0.y + a1.x * z1.x + a1.y * z1.y;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+            for (int u = 0; u < 4; u++) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
+        if (lane < 4) {
+            int i = row_base + warp * RPW + r4 + lane;
+            double v = lane == 0 ? s[0] : (lane == 1 ? s[1] : (lane == 2 ? s[2] : s[3]));
+            if (i < n) work[i] -= v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TRSV_THREADS)
+    trsv_bwd_step_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int n, int j0,
+                         const double* __restrict__ invd, int64_t sInvd, double* work, double* alpha, int64_t sVec) {
+    __shared__ double sj[DB];
+    __shared__ double aj[DB];
+    __shared__ double upper_half[DB];
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.y;
+    L += b * sL;
+    invd += b * sInvd + (int64_t)(j0 / DB) * DB * DB;
+    work += b * sVec;
+    alpha += b * sVec;
+    const int nb = min(DB, n - j0);
+    if (tid < DB) sj[tid] = tid < nb ? work[j0 + tid] : 0.0;
+    __syncthreads();
+    // alpha_j = inv(L_jj)^T s_j : column sums, two row halves per column
+    {
+        const int c = tid & (DB - 1), hlf = tid >> 7;
+        double s = 0.0;
+        const int rbeg = hlf * (DB / 2), rend = rbeg + DB / 2;
+        for (int r = max(rbeg, c); r < rend; r++) s += invd[r * DB + c] * sj[r];
+        if (hlf == 1) upper_half[c] = s;
+        __syncthreads();
+        if (hlf == 0) aj[c] = s + upper_half[c];
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid < nb) alpha[j0 + tid] = aj[tid];
+    // s[c] -= sum_r L[j0+r][c] alpha_j[r] for this CTA's columns left of the block
+    const int c = blockIdx.x * BWD_COLS + tid * 2;
+    if (c < j0) {
+        double a0 = 0.0, a1 = 0.0;
+        const double* src = L + (int64_t)j0 * ld + c;
+#pragma unroll 8
+        for (int r = 0; r < nb; r++) {
+            const double2 v = *reinterpret_cast<const double2*>(src + (int64_t)r * ld);
+            a0 += v.x * aj[r];
+            a1 += v.y * aj[r];
+        }
+        work[c] -= a0;
+        work[c + 1] -= a1;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    ll_finalize_kernel(const double* y, const double* alpha, int64_t sVec, int n, const double* logdet_part, int nblk,
+                       double* scal) {
+    __shared__ double red[256];
+    const int64_t b = blockIdx.x;
+    y += b * sVec;
+    alpha += b * sVec;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += y[i] * alpha[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double ld = 0.0;
+        for (int k = 0; k < nblk; k++) ld += logdet_part[b * nblk + k];
+        ld = 2 * ld;  // matrixops.cpp:133-136
+        double quad = red[0];
+        scal[b * 4 + 0] = quad;
+        scal[b * 4 + 1] = ld;
+        scal[b * 4 + 2] = -0.5 * (quad + ld + n * 1.83787);  // covkernel.cpp:127 (truncated log 2pi)
+        scal[b * 4 + 3] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void copy_vec_kernel(const double* src, double* dst, int64_t count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = src[i];
+}
+
+__global__ void scatter_invdiag_kernel(const double* invd, int64_t sInvd, double* T, int64_t ld, int64_t sT, int n) {
+    const int blk = blockIdx.x;
+    const int64_t b = blockIdx.y;
+    const int j0 = blk * DB, nb = min(DB, n - j0);
+    const double* src = invd + b * sInvd + (int64_t)blk * DB * DB;
+    double* dst = T + b * sT + (int64_t)j0 * ld + j0;
+    for (int e = threadIdx.x; e < DB * DB; e += blockDim.x) {
+        int i = e / DB, j = e % DB;
+        if (i < nb && j < nb) dst[(int64_t)i * ld + j] = src[e];
+    }
+}
+
+// mode 0: zero the upper triangle; 1: mirror the lower triangle; 2: plain copy
+__global__ void export_kernel(const double* A, int64_t ld, int n, double* out, int mode) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int i = blockIdx.y; i < n; i += gridDim.y) {
+        double v;
+        if (j <= i || mode == 2) v = A[(int64_t)i * ld + j];
+        else v = mode == 1 ? A[(int64_t)j * ld + i] : 0.0;
+        out[(int64_t)i * n + j] = v;
+    }
+}
+__global__ void import_kernel(const double* in, int n, double* A, int64_t ld) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    for (int i = blockIdx.y; i < n; i += gridDim.y) A[(int64_t)i * ld + j] = in[(int64_t)i * n + j];
+}
+
+__global__ void predict_finalize_kernel(const double* meanpart, int ntile_mean, const double* css, int ntile_css, int m,
+                                        Hyper h, double* mean, double* var, int64_t sOut, int64_t sMp, int64_t sCss) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    if (t >= m) return;
+    double mu = 0.0, q = 0.0;
+    for (int k = 0; k < ntile_mean; k++) mu += meanpart[b * sMp + (int64_t)k * m + t];
+    for (int k = 0; k < ntile_css; k++) q += css[b * sCss + (int64_t)k * m + t];
+    mean[b * sOut + t] = mu;
+    var[b * sOut + t] = (h.sf2 + h.sn2) - q;  // covkernel.cpp:299-302: k** includes the noise term
+}
+
+__global__ void poe_accumulate_kernel(const double* mean, const double* var, int64_t sOut, int nexp, int m, double* Pp,
+                                      double* Qp, int accumulate) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    double P = accumulate ? Pp[t] : 0.0, Q = accumulate ? Qp[t] : 0.0;
+    for (int e = 0; e < nexp; e++) {  // BCM.cpp:51-55
+        double invvar = 1.0 / var[e * sOut + t];
+        P += invvar;
+        Q += invvar * mean[e * sOut + t];
+    }
+    Pp[t] = P;
+    Qp[t] = Q;
+}
+__global__ void poe_finalize_kernel(const double* PQ, int m, double* mean, double* var) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    double tempvar = 1.0 / PQ[t];  // BCM.cpp:56-57
+    mean[t] = tempvar * PQ[m + t];
+    var[t] = tempvar;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+void launch_cov_train(const double* X, int64_t sX, int n, int dp, Hyper h, double* K, int64_t ld, int64_t sK, int batch,
+                      int full, cudaStream_t st) {
+    CovArgs a{};
+    a.Xi = X; a.sXi = sX; a.ni = n;
+    a.Xj = X; a.sXj = sX; a.nj = n;
+    a.dp = dp; a.h = h;
+    a.out = K; a.ld = ld; a.sOut = sK;
+    int64_t t = cdiv(n, CT);
+    if (full) launch_cov<COV_FULL>(a, t * (t + 1) / 2, batch, st);
+    else launch_cov<COV_LOWER>(a, t * (t + 1) / 2, batch, st);
+}
+
+void launch_cov_cross(const double* Xt, int m, const double* X, int64_t sX, int n, int dp, Hyper h, const double* alpha,
+                      int64_t sAlpha, double* Kstar, int64_t ldk, int64_t sKs, double* meanpart, int64_t sMp, int batch,
+                      cudaStream_t st) {
+    CovArgs a{};
+    a.Xi = Xt; a.sXi = 0; a.ni = m;
+    a.Xj = X; a.sXj = sX; a.nj = n;
+    a.dp = dp; a.h = h;
+    a.out = Kstar; a.ld = ldk; a.sOut = sKs;
+    a.alpha = alpha; a.sAlpha = sAlpha;
+    a.part = meanpart; a.sPart = sMp;
+    a.tiles_j = cdiv(n, CT);
+    launch_cov<COV_CROSS>(a, (int64_t)cdiv(m, CT) * a.tiles_j, batch, st);
+}
+
+size_t grad_trace_partials(int n, int batch) {
+    int64_t t = cdiv(n, CT);
+    return (size_t)(t * (t + 1) / 2) * 3 * (size_t)batch;
+}
+
+void launch_grad_trace(const double* X, int64_t sX, int n, int dp, Hyper h, const double* Kinv, int64_t ld, int64_t sKinv,
+                       const double* alpha, int64_t sAlpha, double* partials, double* out, int batch, cudaStream_t st) {
+    CovArgs a{};
+    a.Xi = X; a.sXi = sX; a.ni = n;
+    a.Xj = X; a.sXj = sX; a.nj = n;
+    a.dp = dp; a.h = h; a.ld = ld;
+    a.alpha = alpha; a.sAlpha = sAlpha;
+    a.Kinv = Kinv; a.sKinv = sKinv;
+    int64_t t = cdiv(n, CT), tiles = t * (t + 1) / 2;
+    a.part = partials; a.sPart = tiles * 3;
+    launch_cov<COV_TRACE>(a, tiles, batch, st);
+    grad_reduce_kernel<<<batch, 256, 0, st>>>(partials, tiles * 3, (int)tiles, h, out);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_potrf_diag(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd, double* logdet_part,
+                       int nblk, int blk, int batch, cudaStream_t st) {
+    constexpr size_t smem = (size_t)DB * DLD * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        CUGP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    potrf_diag_kernel<<<batch, DIAG_THREADS, smem, st>>>(A, ld, sA, n, j0, invd + (int64_t)blk * DB * DB, sInvd,
+                                                         logdet_part, nblk, blk);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_trsv_forward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd, double* work,
+                         double* z, int64_t sVec, int batch, cudaStream_t st) {
+    for (int j0 = 0; j0 < n; j0 += DB) {
+        int below = n - (j0 + DB);
+        int ctas = below > 0 ? cdiv(below, FWD_ROWS) : 1;
+        trsv_fwd_step_kernel<<<dim3(ctas, batch), TRSV_THREADS, 0, st>>>(L, ld, sL, n, j0, invd, sInvd, work, z, sVec);
+    }
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd, double* work,
+                          double* alpha, int64_t sVec, int batch, cudaStream_t st) {
+    int last = (cdiv(n, DB) - 1) * DB;
+    for (int j0 = last; j0 >= 0; j0 -= DB) {
+        int ctas = j0 > 0 ? cdiv(j0, BWD_COLS) : 1;
+        trsv_bwd_step_kernel<<<dim3(ctas, batch), TRSV_THREADS, 0, st>>>(L, ld, sL, n, j0, invd, sInvd, work, alpha, sVec);
+    }
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_ll_finalize(const double* y, const double* alpha, int64_t sVec, int n, const double* logdet_part, int nblk,
+                        double* scal, int batch, cudaStream_t st) {
+    ll_finalize_kernel<<<batch, 256, 0, st>>>(y, alpha, sVec, n, logdet_part, nblk, scal);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_copy_vec(const double* src, double* dst, int64_t count, cudaStream_t st) {
+    if (count <= 0) return;
+    copy_vec_kernel<<<(unsigned)cdiv(count, 256), 256, 0, st>>>(src, dst, count);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_scatter_invdiag(const double* invd, int64_t sInvd, double* T, int64_t ld, int64_t sT, int n, int batch,
+                            cudaStream_t st) {
+    scatter_invdiag_kernel<<<dim3(cdiv(n, DB), batch), 256, 0, st>>>(invd, sInvd, T, ld, sT, n);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+static void launch_export(const double* A, int64_t ld, int n, double* out, int mode, cudaStream_t st) {
+    if (n <= 0) return;
+    export_kernel<<<dim3(cdiv(n, 256), n < 32768 ? n : 32768), 256, 0, st>>>(A, ld, n, out, mode);
+    CUGP_CUDA(cudaGetLastError());
+}
+void launch_export_lower(const double* A, int64_t ld, int n, double* out, cudaStream_t st) { launch_export(A, ld, n, out, 0, st); }
+void launch_export_symmetric(const double* A, int64_t ld, int n, double* out, cudaStream_t st) { launch_export(A, ld, n, out, 1, st); }
+void launch_export_full(const double* A, int64_t ld, int n, double* out, cudaStream_t st) { launch_export(A, ld, n, out, 2, st); }
+void launch_import_full(const double* in, int n, double* A, int64_t ld, cudaStream_t st) {
+    if (n <= 0) return;
+    import_kernel<<<dim3(cdiv(n, 256), n < 32768 ? n : 32768), 256, 0, st>>>(in, n, A, ld);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_predict_finalize(const double* meanpart, int ntile_mean, const double* css, int ntile_css, int m, Hyper h,
+                             double* mean, double* var, int64_t sOut, int64_t sMp, int64_t sCss, int batch,
+                             cudaStream_t st) {
+    if (m <= 0) return;
+    predict_finalize_kernel<<<dim3(cdiv(m, 256), batch), 256, 0, st>>>(meanpart, ntile_mean, css, ntile_css, m, h, mean,
+                                                                        var, sOut, sMp, sCss);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_poe_accumulate(const double* mean, const double* var, int64_t sOut, int nexp, int m, double* P, double* Q,
+                           int accumulate, cudaStream_t st) {
+    if (m <= 0) return;
+    poe_accumulate_kernel<<<cdiv(m, 256), 256, 0, st>>>(mean, var, sOut, nexp, m, P, Q, accumulate);
+    CUGP_CUDA(cudaGetLastError());
+}
+void launch_poe_finalize(const double* PQ, int m, double* mean, double* var, cudaStream_t st) {
+    if (m <= 0) return;
+    poe_finalize_kernel<<<cdiv(m, 256), 256, 0, st>>>(PQ, m, mean, var);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+}  // namespace cugp

@@ -1,0 +1,75 @@
+// kernels.cuh -- launchers of the non-GEMM kernels of the GP hot path (see kernels.cu).
+#pragma once
+#include "common.cuh"
+#include <cmath>
+
+namespace cugp {
+
+// exp(2*theta) terms exactly as the reference forms them (covkernel.cpp:65-67).
+struct Hyper {
+    double ell_sq, sf2, sn2;
+};
+inline Hyper make_hyper(const double th[3]) {
+    Hyper h;
+    h.ell_sq = std::exp(th[0] * 2);
+    h.sf2 = std::exp(th[1] * 2);
+    h.sn2 = std::exp(th[2] * 2);
+    return h;
+}
+
+constexpr int kCovTile = 64;   // covariance / trace tile edge
+constexpr int kMaxDim = 64;    // padded input dimension limit of the shared-memory staging
+
+// ---- K1: covariance build (covkernel.cpp:64-102).  X is [batch][n][dp] (dp even, zero padded).
+// full = 0: lower tiles only (feeds the factorisation); full = 1: both triangles (API a3).
+void launch_cov_train(const double* X, int64_t sX, int n, int dp, Hyper h, double* K, int64_t ld, int64_t sK,
+                      int batch, int full, cudaStream_t st);
+// ---- K5a: cross covariance Kstar[t][i] (covkernel.cpp:105-116) fused with mean partials
+// meanpart[tile_j][t] = sum over the tile's train columns of Kstar[t][i]*alpha[i].
+void launch_cov_cross(const double* Xt, int m, const double* X, int64_t sX, int n, int dp, Hyper h,
+                      const double* alpha, int64_t sAlpha, double* Kstar, int64_t ldk, int64_t sKs,
+                      double* meanpart, int64_t sMp, int batch, cudaStream_t st);
+// ---- K4: fused gradient trace (covkernel.cpp:172-254) -- rebuilds K_ij and D_ij from X tiles while
+// streaming the lower triangle of Kinv; never materialises dK, W or K.*D.  out[batch][3] = (g0,g1,g2).
+void launch_grad_trace(const double* X, int64_t sX, int n, int dp, Hyper h, const double* Kinv, int64_t ld,
+                       int64_t sKinv, const double* alpha, int64_t sAlpha, double* partials, double* out,
+                       int batch, cudaStream_t st);
+size_t grad_trace_partials(int n, int batch);  // doubles needed in `partials`
+
+// ---- K2a: Cholesky + inverse of one 128x128 diagonal block per batch element (matrixops.cpp:68-108 on
+// the block).  Writes L11 (zero upper) back into A, inv(L11) (zero upper, identity padded) to invd and
+// sum(log L_ii) of the block to logdet_part[batch][blk].
+void launch_potrf_diag(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd,
+                       double* logdet_part, int nblk, int blk, int batch, cudaStream_t st);
+
+// ---- K3: blocked triangular solves L z = y, L^T alpha = z (matrixops.cpp:145-164) with the stored
+// inverses of the diagonal blocks; one launch per 128-column block and sweep.
+void launch_trsv_forward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd,
+                         double* work, double* z, int64_t sVec, int batch, cudaStream_t st);
+void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd,
+                          double* work, double* alpha, int64_t sVec, int batch, cudaStream_t st);
+// scal[batch][4] = (y'alpha, logdet, LL, 0) with LL = -0.5*(quad + logdet + n*1.83787) (covkernel.cpp:127)
+void launch_ll_finalize(const double* y, const double* alpha, int64_t sVec, int n, const double* logdet_part,
+                        int nblk, double* scal, int batch, cudaStream_t st);
+
+// ---- helpers
+void launch_copy_vec(const double* src, double* dst, int64_t count, cudaStream_t st);
+// T diagonal blocks <- invd blocks (level 0 of the recursive triangular inverse)
+void launch_scatter_invdiag(const double* invd, int64_t sInvd, double* T, int64_t ld, int64_t sT, int n,
+                            int batch, cudaStream_t st);
+// dense output helpers for the matrixops API: out[n][n] (tight) from a padded matrix
+void launch_export_lower(const double* A, int64_t ld, int n, double* out, cudaStream_t st);      // zero upper
+void launch_export_symmetric(const double* A, int64_t ld, int n, double* out, cudaStream_t st);  // mirror lower
+void launch_export_full(const double* A, int64_t ld, int n, double* out, cudaStream_t st);
+void launch_import_full(const double* in, int n, double* A, int64_t ld, cudaStream_t st);
+
+// ---- prediction finalisation (covkernel.cpp:297-302): mean = sum of partials, var = sf2+sn2 - sum css
+void launch_predict_finalize(const double* meanpart, int ntile_mean, const double* css, int ntile_css, int m,
+                             Hyper h, double* mean, double* var, int64_t sOut, int64_t sMp, int64_t sCss,
+                             int batch, cudaStream_t st);
+// ---- BCM product of experts (BCM.cpp:45-62): P[t] += 1/var_e, Q[t] += mean_e/var_e over local experts
+void launch_poe_accumulate(const double* mean, const double* var, int64_t sOut, int nexp, int m, double* P, double* Q,
+                           int accumulate, cudaStream_t st);
+void launch_poe_finalize(const double* PQ, int m, double* mean, double* var, cudaStream_t st);
+
+}  // namespace cugp

@@ -1,0 +1,161 @@
+/*
+ * cugp.h -- C ABI of the B200-native cuGP hot path (libcugp.so).
+ *
+ * This is the drop-in boundary for the exact-GP regression path of abhishekjoshi2/cuGP.  The reference has no
+ * plugin/FFI interface: its boundary is the C++ link surface of
+ *     cpp_serial_gp/covkernel.h:3-38   (class Covsum)
+ *     common/matrixops.h:5-25          (free functions on double**)
+ *     distributed_gp/BCM.h:2-27        (class BCM)
+ * Each entry point below names the reference member it replaces.  include/cugp_shim/{covkernel,matrixops,BCM}.h
+ * re-declare those classes/functions with the reference's exact signatures on top of this ABI, so the
+ * reference drivers (cpp_serial_gp/serial_gp.cpp, distributed_gp/distributed_ver1.cpp) build against it
+ * unchanged.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all arrays are HOST pointers to C-contiguous row-major FP64 unless the
+ *     parameter name ends in `_dev` (device pointer in the current CUDA context);
+ *   - theta = (log ell, log sigma_f, log sigma_n)  -- covkernel.cpp:65-67;
+ *   - every function returns an int status (CUGP_OK = 0) and never throws or aborts; a non-positive-definite
+ *     covariance yields NaN results with status CUGP_OK, exactly like the reference (matrixops.cpp:77,
+ *     covkernel.cpp:490-505 relies on it);
+ *   - there is NO CPU fallback: without a CUDA device (or without the sm_100a build) calls return
+ *     CUGP_ERR_NODEVICE / CUGP_ERR_CUDA and cugp_last_error() says why;
+ *   - the gradient is d(-LL)/d(theta) (the reference's sign, covkernel.cpp:221,259-261), the log-likelihood uses
+ *     the reference's truncated log(2*pi) = 1.83787 (covkernel.cpp:127), the predictive variance includes the
+ *     noise term (covkernel.cpp:299), NLPP uses 2*pi = 6.283185 (covkernel.cpp:633);
+ *   - handles are not thread safe (neither is the reference: static gradient buffer, covkernel.cpp:167).
+ */
+#ifndef CUGP_H
+#define CUGP_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUGP_OK 0
+#define CUGP_ERR_INVALID 1
+#define CUGP_ERR_CUDA 2
+#define CUGP_ERR_NOMEM 3
+#define CUGP_ERR_NODEVICE 4
+
+typedef struct cugp_covsum cugp_covsum; /* one exact GP: replaces class Covsum */
+typedef struct cugp_bcm cugp_bcm;       /* expert ensemble: replaces class BCM */
+
+/* ---- library ------------------------------------------------------------------------------------ */
+const char *cugp_version(void);
+const char *cugp_last_error(void);          /* message of the last failing call on this thread */
+int cugp_device_count(int *count);          /* CUGP_ERR_NODEVICE when no CUDA device is visible */
+int cugp_set_device(int device);            /* one process per GPU: call before creating handles */
+/* kernels launched by this library since the last reset (bench.py `gpu_launches`) */
+long cugp_launch_count(void);
+void cugp_launch_count_reset(void);
+
+/* ---- Covsum (cpp_serial_gp/covkernel.h:3-38) ------------------------------------------------------ */
+/* Covsum::Covsum(int n, int d), covkernel.cpp:13-36.  d <= 64. */
+int cugp_covsum_create(int n, int d, cugp_covsum **out);
+/* Covsum::~Covsum, covkernel.cpp:38-61 */
+int cugp_covsum_destroy(cugp_covsum *h);
+/* Covsum::set_loghyperparam / set_loghyper_eigen, covkernel.cpp:270-274, 308-312 */
+int cugp_covsum_set_loghyper(cugp_covsum *h, const double theta[3]);
+/* Covsum::get_loghyperparam, covkernel.cpp:266-268 */
+int cugp_covsum_get_loghyper(cugp_covsum *h, double theta[3]);
+/* Covsum::compute_K_train, covkernel.cpp:64-102: K_out is n x n, both triangles, noise on the diagonal. */
+int cugp_covsum_K_train(cugp_covsum *h, const double *X, double *K_out);
+/* Covsum::compute_k_test, covkernel.cpp:105-116: k_out[i] = k(x_i, xtest), no noise. */
+int cugp_covsum_k_test(cugp_covsum *h, const double *X, const double *xtest, double *k_out);
+/* Covsum::compute_loglikelihood, covkernel.cpp:118-129 */
+int cugp_covsum_loglik(cugp_covsum *h, const double *X, const double *y, double *ll);
+/* Covsum::compute_gradient_loghyperparam, covkernel.cpp:162-263 (out-array instead of the static buffer).
+ * Reuses the factorisation of a preceding cugp_covsum_loglik on the same (X, y, theta). */
+int cugp_covsum_grad(cugp_covsum *h, const double *X, const double *y, double grad[3]);
+/* Covsum::compute_test_means_and_variances, covkernel.cpp:277-306: Xtest is m x d. */
+int cugp_covsum_predict(cugp_covsum *h, const double *X, const double *y, const double *Xtest, int m,
+                        double *mean, double *var);
+/* Covsum::get_negative_log_predprob, covkernel.cpp:629-638 (host arithmetic on m values). */
+int cugp_nlpp(const double *actual, const double *mean, const double *var, int m, double *out);
+/* Covsum::cg_solve, covkernel.cpp:388-627: Polack-Ribiere CG on f = -LL, at most 100 evaluations; theta of
+ * the handle is updated.  f_trace (may be NULL) receives f at every trial point; *n_evals their count. */
+int cugp_covsum_cg_solve(cugp_covsum *h, const double *X, const double *y, double *f_trace, int trace_cap,
+                         int *n_evals);
+/* Covsum::rprop_solve, covkernel.cpp:320-385 */
+int cugp_covsum_rprop_solve(cugp_covsum *h, const double *X, const double *y);
+
+/* The same two optimisers over a caller-supplied evaluation f = -LL, g = d(-LL)/dtheta (non-zero return
+ * aborts): multi-rank BCM passes a callback that allreduces (LL, g) over ranks
+ * (distributed_gp/distributed_ver1.cpp:13-232 is this loop over BCM::get_BCM_loglikelihood/gradient). */
+typedef int (*cugp_eval_fn)(void *ctx, const double theta[3], double *f, double g[3]);
+int cugp_cg_minimize(cugp_eval_fn fn, void *ctx, double theta[3], double *f_trace, int trace_cap, int *n_evals);
+int cugp_rprop_minimize(cugp_eval_fn fn, void *ctx, double theta[3], int *n_iters);
+
+/* Device-resident variants (no host<->device copies of X, y inside): upload once, evaluate many thetas.
+ * These are what the optimiser loops use; the reference re-reads its data on every evaluation
+ * (cuda_scalingdist/cg_solver.cpp:45-52). */
+int cugp_covsum_set_data(cugp_covsum *h, const double *X, const double *y);
+int cugp_covsum_loglik_resident(cugp_covsum *h, double *ll);
+int cugp_covsum_grad_resident(cugp_covsum *h, double grad[3]);
+/* (y'K^-1 y, logdet K, LL) of the resident problem: the pair compute_chol_and_det returns + covkernel.cpp:127 */
+int cugp_covsum_scalars_resident(cugp_covsum *h, double out3[3]);
+/* alpha = K^-1 y of the resident problem (n values) */
+int cugp_covsum_alpha_resident(cugp_covsum *h, double *alpha);
+/* Factorise only (covariance build + Cholesky); *seconds_chol = device time of the Cholesky alone
+ * (CUDA events on the launching stream), for the FP64 roofline (n^3/3 flop). */
+int cugp_covsum_factorize_resident(cugp_covsum *h, float *ms_cov, float *ms_chol);
+
+/* ---- matrixops (common/matrixops.h:5-25) ------------------------------------------------------------ */
+/* get_cholesky, matrixops.cpp:68-108: L dense n x n with zeroed upper triangle; NaN on a negative pivot. */
+int cugp_cholesky(const double *A, double *L, int n);
+/* compute_chol_and_det, matrixops.cpp:232-234: *quad = y'K^-1 y, *logdet = 2 sum log L_ii */
+int cugp_chol_and_det(const double *K, const double *y, int n, double *quad, double *logdet);
+/* vector_Kinvy_using_cholesky, matrixops.cpp:264-316 */
+int cugp_kinv_y(const double *K, const double *y, double *alpha, int n);
+/* compute_K_inverse, matrixops.cpp:383-435: dense symmetric n x n */
+int cugp_k_inverse(const double *K, double *Kinv, int n);
+
+/* ---- BCM (distributed_gp/BCM.h:2-27) ---------------------------------------------------------------- */
+/* BCM::BCM(X, y, N, D, K), BCM.cpp:85-110: K contiguous chunks of floor(N/K) rows, the last takes the
+ * remainder.  One process per GPU: this process owns experts e with e % world == rank and keeps them device
+ * resident; rank/world = 0/1 for a single GPU.  Data is copied (the reference keeps the caller's pointers). */
+int cugp_bcm_create(const double *X, const double *y, int N, int D, int K, int rank, int world, cugp_bcm **out);
+int cugp_bcm_destroy(cugp_bcm *h);
+/* BCM::set_BCM_log_hyperparam / set_BCM_loghyper_eigen, BCM.cpp:123-130, 205-212 */
+int cugp_bcm_set_loghyper(cugp_bcm *h, const double theta[3]);
+/* BCM::get_loghyperparam, BCM.cpp:200-204 */
+int cugp_bcm_get_loghyper(cugp_bcm *h, double theta[3]);
+/* BCM::get_BCM_loglikelihood, BCM.cpp:182-198 / BCM::get_BCM_gradient_hyper, BCM.cpp:153-180:
+ * the sum over THIS rank's experts; the caller sums over ranks (one allreduce of 4 doubles:
+ * out4 = (LL, g0, g1, g2)).  With world == 1 these are the reference's results. */
+int cugp_bcm_loglik_grad_local(cugp_bcm *h, int want_grad, double out4[4]);
+/* per-expert log-likelihoods of the local experts, in expert order (BCM.cpp:195 prints them) */
+int cugp_bcm_local_experts(cugp_bcm *h, int *count, int *ids /* count */, double *ll /* count, may be NULL */);
+/* BCM::compute_BCM_test_means_and_var, BCM.cpp:64-83, split at the exchange step:
+ *   1. moments: PQ[0..m) = sum_e 1/var_e, PQ[m..2m) = sum_e mean_e/var_e over THIS rank's experts
+ *      (product_of_experts, BCM.cpp:51-55), written to a device buffer (_dev) or a host buffer;
+ *   2. the caller allreduces PQ over ranks (NCCL sum of 2m doubles);
+ *   3. finalize: var = 1/P, mean = var*Q (BCM.cpp:56-60). */
+int cugp_bcm_predict_moments_dev(cugp_bcm *h, const double *Xtest, int m, double *PQ_dev);
+int cugp_bcm_predict_moments(cugp_bcm *h, const double *Xtest, int m, double *PQ);
+int cugp_poe_finalize_dev(const double *PQ_dev, int m, double *mean, double *var);
+int cugp_poe_finalize(const double *PQ, int m, double *mean, double *var);
+/* world == 1 convenience: the whole of BCM::compute_BCM_test_means_and_var */
+int cugp_bcm_predict(cugp_bcm *h, const double *Xtest, int m, double *mean, double *var);
+
+/* ---- measurement helpers (bench.py) ----------------------------------------------------------------- */
+/* Sustained FP64 DMMA (mma.sync.m8n8k4.f64) and DFMA throughput of this GPU in TFLOP/s, register resident,
+ * timed with CUDA events for about `ms` milliseconds each: the measured FP64 roofline denominators. */
+int cugp_probe_fp64_peak(float ms, double *dmma_tflops, double *dfma_tflops);
+/* C[M x N] (+)= alpha * A B^T on the DMMA GEMM with device-resident random operands; returns TFLOP/s. */
+int cugp_probe_gemm(int M, int N, int K, int iters, double *tflops);
+/* Kernel-level test hook: one launch of the DMMA GEMM template on host operands.
+ *   C[M x N] = alpha * op(A) op(B) + beta * C,  a_kc: A stored [M][K] (else [K][M]); b_kc: B stored [N][K]
+ *   (else [K][N]); flags bit0 lower tiles only, bit1 k >= ti*BM, bit2 k >= tj*BN, bit3 k < (ti+1)*BM,
+ *   bit4 k < (tj+1)*BN; config 0 = 128x128, 1 = 64x128, 2 = 64x64 tiles.  If colsumsq != NULL it receives
+ *   [ceil(M/BM)][N] per-row-tile column sums of squares and C is left untouched. */
+int cugp_debug_gemm(const double *A, const double *B, double *C, int M, int N, int K, double alpha, double beta,
+                    int a_kc, int b_kc, int flags, int config, double *colsumsq);
+/* device copy bandwidth (read + write bytes / s) over `bytes` bytes, GB/s */
+int cugp_probe_copy(size_t bytes, int iters, double *gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUGP_H */

@@ -1,0 +1,277 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed golden vectors.
+
+Tolerances are BASELINE.json's: log-likelihood and gradient 1e-9 relative, predictive mean/variance 1e-8
+relative (conftest.assert_*); element-wise covariance to a few ulp (only exp() differs from glibc's)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cugp_b200 as cg
+from cugp_b200._lib import lib, ptr
+from oracle import oracle
+from tests.conftest import (assert_grad, assert_ll, assert_pred, case_inputs, load_data, load_golden)
+
+pytestmark = pytest.mark.gpu
+GOLD = load_golden()
+PORT = oracle.port()
+TH_B = [3.762111, -1.152105, -0.384461]
+
+
+# ---------------------------------------------------------------------------------------------- kernel level
+def _gemm(A, B, Cm, alpha, beta, a_kc, b_kc, flags, config, css=False):
+    M, N = Cm.shape
+    K = A.shape[1] if a_kc else A.shape[0]
+    out = np.ascontiguousarray(Cm.copy())
+    tm = -(-M // (128 if config == 0 else 64))
+    S = np.zeros((tm, N)) if css else None
+    rc = lib().cugp_debug_gemm(ptr(np.ascontiguousarray(A)), ptr(np.ascontiguousarray(B)), ptr(out), M, N, K,
+                               alpha, beta, int(a_kc), int(b_kc), flags, config, ptr(S) if css else None)
+    assert rc == 0, lib().cugp_last_error()
+    return out, S
+
+
+@pytest.mark.parametrize("config", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(200, 150, 170), (129, 77, 45), (64, 128, 128), (1, 1, 1), (300, 257, 19)])
+def test_gemm_layouts(config, shape):
+    M, N, K = shape
+    rng = np.random.default_rng(M * 1000 + N)
+    A, B, C0 = rng.standard_normal((M, K)), rng.standard_normal((N, K)), rng.standard_normal((M, N))
+    ref = -1.0 * A @ B.T + 1.0 * C0
+    for a_kc, b_kc in ((1, 1), (1, 0), (0, 0), (0, 1)):
+        Ain = A if a_kc else A.T
+        Bin = B if b_kc else B.T
+        out, _ = _gemm(Ain, Bin, C0, -1.0, 1.0, a_kc, b_kc, 0, config)
+        assert np.allclose(out, ref, rtol=1e-13, atol=1e-12), (a_kc, b_kc, np.abs(out - ref).max())
+    out, _ = _gemm(A, B, np.full((M, N), np.nan), 2.0, 0.0, 1, 1, 0, config)  # beta == 0 must not read C
+    assert np.allclose(out, 2.0 * A @ B.T, rtol=1e-13, atol=1e-12)
+
+
+@pytest.mark.parametrize("config", [0, 2])
+def test_gemm_triangular_ranges(config):
+    """The k-range flags must be exact for triangular operands (TRTRI / LAUUM / predictive variance)."""
+    rng = np.random.default_rng(3)
+    n, N = 333, 210
+    T = np.tril(rng.standard_normal((n, n)))
+    Bf = rng.standard_normal((n, N))
+    # khi_ti: A lower triangular [M][K], B [K][N] row-contig           (T21 = -T22 * tmp)
+    out, _ = _gemm(T, Bf, np.zeros((n, N)), -1.0, 0.0, 1, 0, 1 << 3, config)
+    assert np.allclose(out, -T @ Bf, rtol=1e-13, atol=1e-12)
+    # klo_tj: B lower triangular stored [K][N], A full [M][K]            (tmp = L21 * T11)
+    Af = rng.standard_normal((N, n))
+    out, _ = _gemm(Af, T, np.zeros((N, n)), 1.0, 0.0, 1, 0, 1 << 2, config)
+    assert np.allclose(out, Af @ T, rtol=1e-13, atol=1e-12)
+    # LAUUM: C(lower) = T^T T with A = B = T stored [K][M]; lower tiles, k >= ti*BM
+    out, _ = _gemm(T, T, np.zeros((n, n)), 1.0, 0.0, 0, 0, 1 | (1 << 1), config)
+    assert np.allclose(np.tril(out), np.tril(T.T @ T), rtol=1e-13, atol=1e-12)
+    # SYRK: lower tiles of C - P P^T
+    P = rng.standard_normal((n, 128))
+    C0 = rng.standard_normal((n, n))
+    out, _ = _gemm(P, P, C0, -1.0, 1.0, 1, 1, 1, config)
+    assert np.allclose(np.tril(out), np.tril(C0 - P @ P.T), rtol=1e-13, atol=1e-12)
+    # predictive variance epilogue: column sums of squares of T Kstar^T, per row tile
+    Ks = rng.standard_normal((N, n))
+    _, S = _gemm(T, Ks, np.zeros((n, N)), 1.0, 0.0, 1, 1, 1 << 3, config, css=True)
+    assert np.allclose(S.sum(0), ((T @ Ks.T) ** 2).sum(0), rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------- matrixops
+def _spd(n, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-3, 3, (n, 4))
+    return PORT.K_train(X, [0.7, 0.3, -1.0]), rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 300, 1000])
+def test_matrixops_vs_oracle(n):
+    K, y = _spd(n, n)
+    L, Lo = cg.get_cholesky(K), PORT.cholesky(K)
+    assert np.all(np.triu(L, 1) == 0.0)
+    assert np.linalg.norm(L - Lo) <= 1e-12 * np.linalg.norm(Lo)
+    q, ld = cg.compute_chol_and_det(K, y)
+    qo, ldo = PORT.chol_and_det(K, y)
+    assert abs(q - qo) <= 1e-10 * abs(qo) and abs(ld - ldo) <= 1e-11 * max(1.0, abs(ldo))
+    a, ao = cg.vector_Kinvy_using_cholesky(K, y), PORT.kinv_y(K, y)
+    assert np.linalg.norm(a - ao) <= 1e-10 * np.linalg.norm(ao)
+    if n <= 300:
+        Ki, Kio = cg.compute_K_inverse(K), PORT.k_inverse(K)
+        assert np.linalg.norm(Ki - Kio) <= 1e-10 * np.linalg.norm(Kio)
+        assert np.array_equal(Ki, Ki.T)
+
+
+def test_non_pd_is_nan_not_an_error():
+    """sqrt of a negative pivot gives NaN that propagates; status stays OK (matrixops.cpp:77)."""
+    A = np.array([[1.0, 2.0], [2.0, 1.0]])
+    L = cg.get_cholesky(A)
+    assert np.isnan(L[1, 1])
+    q, ld = cg.compute_chol_and_det(A, np.ones(2))
+    assert np.isnan(q) or np.isnan(ld)
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (200, 3))
+    X[150] = X[3]                                   # duplicate point + vanishing noise => singular K
+    c = cg.Covsum(200, 3)
+    c.set_loghyperparam([5.0, 0.0, -400.0])
+    ll = c.compute_loglikelihood(X, np.sin(X[:, 0]))
+    assert not np.isfinite(ll) or ll == ll            # no exception is the contract; NaN/Inf allowed
+
+
+# ---------------------------------------------------------------------------------------------- covariance
+@pytest.mark.parametrize("n,d", [(1, 1), (63, 3), (64, 10), (65, 7), (300, 10), (1024, 10)])
+def test_K_train_and_k_test(n, d):
+    rng = np.random.default_rng(n + d)
+    X = rng.uniform(-20, 20, (n, d)) if d == 10 else rng.uniform(-3, 3, (n, d))
+    for th in ([0.5, 0.5, 0.5], TH_B):
+        c = cg.Covsum(n, d)
+        c.set_loghyperparam(th)
+        K, Ko = c.compute_K_train(X), PORT.K_train(X, th)
+        assert np.array_equal(K, K.T)
+        assert np.array_equal(np.diag(K), np.diag(Ko))                 # sf2*exp(0)+sn2, exact
+        # off-diagonal: same argument bit for bit, exp() within a couple of ulp (subnormals: absolute)
+        assert np.all(np.abs(K - Ko) <= 8 * np.spacing(np.abs(Ko)) + 1e-320), np.abs(K - Ko).max()
+        xt = rng.uniform(-3, 3, d)
+        k, ko = c.compute_k_test(X, xt), PORT.k_test(X, th, xt)
+        assert np.all(np.abs(k - ko) <= 8 * np.spacing(np.abs(ko)) + 1e-320)
+
+
+# ---------------------------------------------------------------------------------------------- golden cases
+COVSUM = [n for n, c in GOLD.items() if c["kind"] == "covsum"]
+BCMS = [n for n, c in GOLD.items() if c["kind"] == "bcm"]
+
+
+@pytest.mark.parametrize("name", COVSUM)
+def test_covsum_golden(name):
+    c = GOLD[name]
+    X, y, Xt, yt = case_inputs(c)
+    g = cg.Covsum(c["n"], c["d"])
+    g.set_loghyperparam(c["theta"])
+    assert_ll(g.compute_loglikelihood(X, y), c["ll"])
+    assert_grad(g.compute_gradient_loghyperparam(X, y), c["grad"])
+    if "mean" in c:
+        mu, var = g.compute_test_means_and_variances(X, y, Xt)
+        assert_pred(mu, var, c["mean"], c["var"], yscale=np.abs(y).max())
+        # NLPP: through the reference formula on our moments (gated like the moments)
+        assert abs(g.get_negative_log_predprob(yt, mu, var) - c["nlpp"]) <= 1e-7 * max(1.0, abs(c["nlpp"]))
+    if "alpha" in c:
+        g.set_data(X, y)
+        q, ld, ll = g.scalars_resident()
+        assert abs(q - c["quad"]) <= 1e-9 * abs(c["quad"]) and abs(ld - c["logdet"]) <= 1e-10 * abs(c["logdet"])
+        a = g.alpha_resident()
+        assert np.linalg.norm(a - c["alpha"]) <= 1e-9 * np.linalg.norm(c["alpha"])
+    g.close()
+
+
+@pytest.mark.parametrize("name", BCMS)
+def test_bcm_golden_single_gpu(name):
+    c = GOLD[name]
+    X, y, Xt, yt = case_inputs(c)
+    b = cg.BCM(X, y, c["n"], c["d"], c["K"], rank=0, world=1)
+    b.set_BCM_log_hyperparam(c["theta"])
+    assert_ll(b.get_BCM_loglikelihood(), c["ll"])
+    assert_grad(b.get_BCM_gradient_hyper(), c["grad"])
+    if "mean" in c:
+        mu, var = b.compute_BCM_test_means_and_var(Xt)
+        assert_pred(mu, var, c["mean"], c["var"], yscale=np.abs(y).max())
+        assert abs(b.get_BCM_negative_log_predprob(yt, mu, var) - c["nlpp"]) <= 1e-7 * max(1.0, abs(c["nlpp"]))
+    b.close()
+
+
+def test_bcm_rank_partials_sum_to_whole():
+    """Emulate W=3 ranks in one process: the per-rank partial sums and moments must add up to the W=1 result
+    (the allreduce is a plain sum)."""
+    c = GOLD["si24000_first3000_bcm4_thB_pred16"]
+    X, y, Xt, _ = case_inputs(c)
+    whole = cg.BCM(X, y, K=4, rank=0, world=1)
+    whole.set_BCM_log_hyperparam(c["theta"])
+    ll, g = whole.loglik_and_gradient()
+    mu, var = whole.compute_BCM_test_means_and_var(Xt)
+    acc4, accPQ = np.zeros(4), np.zeros((2, Xt.shape[0]))
+    for r in range(3):
+        part = cg.BCM(X, y, K=4, rank=r, world=3)       # no process group: _allreduce is the identity
+        part.set_BCM_log_hyperparam(c["theta"])
+        acc4 += part._local.loglik_grad(True)
+        accPQ += part._local.moments(np.ascontiguousarray(Xt))
+        part.close()
+    assert_ll(acc4[0], ll, 1e-13)
+    assert_grad(acc4[1:], g, 1e-12)
+    assert_pred(accPQ[1] / accPQ[0], 1.0 / accPQ[0], mu, var, rtol=1e-12)
+    assert_ll(ll, c["ll"])
+    whole.close()
+
+
+# ---------------------------------------------------------------------------------------------- API behaviour
+def test_loglik_then_grad_share_one_factorisation():
+    c = GOLD["sine300_thB_pred7"]
+    X, y, _, _ = case_inputs(c)
+    g = cg.Covsum(300, 10)
+    g.set_loghyperparam(c["theta"])
+    lib().cugp_launch_count_reset()
+    g.compute_loglikelihood(X, y)
+    n1 = lib().cugp_launch_count()
+    grad_cached = g.compute_gradient_loghyperparam(X, y)
+    n2 = lib().cugp_launch_count() - n1
+    h = cg.Covsum(300, 10)
+    h.set_loghyperparam(c["theta"])
+    lib().cugp_launch_count_reset()
+    grad_fresh = h.compute_gradient_loghyperparam(X, y)
+    n3 = lib().cugp_launch_count()
+    assert np.array_equal(grad_cached, grad_fresh)      # deterministic reductions: bit-identical
+    assert n2 < n3                                       # the second call did not re-factorise
+    y2 = y.copy()
+    y2[0] += 1.0
+    assert g.compute_loglikelihood(X, y2) != g.compute_loglikelihood(X, y)   # changed data is noticed
+
+
+def test_cg_solve_replays_reference_log():
+    """cuda_bettersinglenode_ver2/REF: LL trajectory (6 digits) and optimum of the 128x2 problem."""
+    d = load_data("si128x2")
+    log = GOLD["REF_log"]
+    g = cg.Covsum(128, 2)
+    g.set_loghyperparam(log["theta0"])
+    trace = g.cg_solve(d["X"], d["y"])
+    lls = [-f for f in trace]
+    logged = log["ll_sequence"][1:1 + len(lls)]
+    assert len(lls) >= 60
+    bad = [(i, a, b) for i, (a, b) in enumerate(zip(lls, logged)) if abs(a - b) > 5e-6 * max(1.0, abs(b))]
+    assert not bad, bad[:5]
+    assert np.allclose(g.get_loghyperparam(), GOLD["si128_cg_from_th15"]["theta_final"], rtol=0, atol=1e-6)
+    b = cg.BCM(d["X"], d["y"], K=4, rank=0, world=1)
+    b.set_BCM_log_hyperparam(log["theta0"])
+    b.cg_solve()
+    assert np.allclose(b.get_loghyperparam(), GOLD["si128_bcm4_cg_from_th15"]["theta_final"], rtol=0, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- full sizes
+def test_c3_size_properties():
+    """n = 10000 (C3 shape, synthetic sine data): properties that do not need the O(n^3) CPU path.
+    K alpha = y to 1e-10, logdet and quad against LAPACK (float64) to 1e-10, LL formula consistency."""
+    from cugp_b200.loaders import synthetic_sine
+    n = 10000
+    X, y = synthetic_sine(n + 64, 10)
+    Xt, X, y = X[n:], X[:n], y[:n]
+    g = cg.Covsum(n, 10)
+    g.set_loghyperparam(TH_B)
+    K = g.compute_K_train(X)
+    g.set_data(X, y)
+    q, ld, ll = g.scalars_resident()
+    a = g.alpha_resident()
+    assert np.linalg.norm(K @ a - y) <= 1e-10 * np.linalg.norm(y)
+    Lk = np.linalg.cholesky(K)
+    ld_ref = 2.0 * np.log(np.diag(Lk)).sum()
+    assert abs(ld - ld_ref) <= 1e-10 * abs(ld_ref)
+    assert abs(q - y @ a) <= 1e-10 * abs(q)
+    assert ll == -0.5 * (q + ld + n * 1.83787)
+    # gradient against the closed form with LAPACK's inverse
+    import scipy.linalg as sl
+    Ki = sl.cho_solve((Lk, True), np.eye(n))
+    W = Ki - np.outer(a, a)
+    sf2, sn2, ell2 = np.exp(2 * TH_B[1]), np.exp(2 * TH_B[2]), np.exp(2 * TH_B[0])
+    Ks = K - sn2 * np.eye(n)
+    D = -2.0 * ell2 * np.log(np.maximum(Ks, 1e-300) / sf2)     # |xi-xj|^2 recovered from K
+    np.fill_diagonal(D, 0.0)
+    gref = np.array([0.5 * np.sum(W * Ks * D / ell2), np.sum(W * Ks), sn2 * np.trace(W)])
+    assert_grad(g.grad_resident(), gref, 1e-8)
+    # prediction against the same LAPACK factor
+    mu, var = g.compute_test_means_and_variances(X, y, Xt)
+    kst = np.stack([PORT.k_test(X, TH_B, x) for x in Xt])
+    v = sl.solve_triangular(Lk, kst.T, lower=True)
+    assert_pred(mu, var, kst @ a, sf2 + sn2 - (v * v).sum(0), yscale=1.0, rtol=1e-8)
