@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200, one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c3|c2|c4] [--n ROWS] [--impl reference]
+
+Metric (BASELINE.json): "FP64 Cholesky TFLOP/s (% peak); loglik+grad evals/s; BCM pred pts/s at 1-8 GPU".
+The default workload is C5, the configuration the Cholesky figure is quoted on and the largest that fits one
+GPU: synthetic exact GP, n = 100 000, d = 10 (K is 80 GB of FP64).  A step is one training pass of the hot
+path on device-resident inputs: covariance build (lower triangle) -> blocked Cholesky -> forward/backward
+solves -> log-likelihood.  `value` = (n^3/3 flop) / step time, the flop count of the factorisation
+(SURVEY.md section 8(d)); the `extra` block carries the other two parts of the metric (C2 evals/s, C4 pts/s).
+
+  --workload c3  exact GP n = 10 000 (train + predict), same metric
+  --workload c2  n = 4096 hyper-parameter loop: value = (LL + gradient) evaluations / s
+  --workload c4  BCM 16 x 1500 on N ranks (experts sharded, NCCL allreduce of the moments): value = pts/s
+
+Multi-GPU: the exact GP does not shard -- N ranks run N independent replicas
+("weak"); c4 shards the 16 experts over the ranks ("strong").  Timing: W >= 3 warm-ups, then K steps between
+barrier + cuda synchronize, device time with CUDA events, max over ranks.  Inputs of every workload are far
+larger than the 126 MB L2 except c2/c4, where an L2 flush (256 MB write) runs between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TH_B = [3.762111, -1.152105, -0.384461]   # trained values, cuda_src/main.cpp:191-193
+TH_C = [2.0, 2.0, 2.0]                    # cuda_scalingdist/main.cpp:298-301
+NOMINAL_FP64_TFLOPS = 37.0                # HGX B200 data sheet, dense FP64 (tensor = vector)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    """One process per GPU (torchrun env).  Returns (rank, world, torch, dist or None)."""
+    import torch
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, torch, dist
+
+
+def timed_steps(torch, dist, step, steps, warmup, flush=None):
+    """W warm-ups, then K steps between barrier + synchronize; device time via CUDA events; max over ranks."""
+    for _ in range(warmup):
+        step()
+        if flush is not None:
+            flush()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total_ms = 0.0
+    t_wall = time.perf_counter()
+    for _ in range(steps):
+        # the library runs on its own stream and synchronises before returning, so events recorded on the
+        # current stream around the (blocking) call bracket the device work of the step
+        e0.record()
+        step()
+        e1.record()
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        if flush is not None:
+            flush()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    ms = total_ms / steps
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, wall_ms / steps
+
+
+def make_flush(torch):
+    buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush():
+        buf.add_(1)  # write 256 MB > 126 MB L2
+
+    return flush
+
+
+# --------------------------------------------------------------------------------------------------------------
+def cpu_baseline(kind_pref: str, n_s: int, theta, reps: int = 1):
+    """The reference's CPU path timed on this host: compute_loglikelihood (K build + Cholesky + solves) on a
+    bounded sample of the same synthetic workload; TFLOP/s at n_s^3/3.  Single thread: the reference has no
+    threading."""
+    from cugp_b200.loaders import synthetic_sine
+    from oracle import oracle
+    impl = oracle.reference() if kind_pref == "reference" else None
+    if impl is None:
+        impl = oracle.port()
+    X, y = synthetic_sine(n_s, 10)
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        ll = impl.loglik(X, y, theta)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    return {"value": (n_s ** 3 / 3) / best / 1e12, "unit": "TFLOP/s", "cores": 1, "kind": impl.kind,
+            "sample": f"one compute_loglikelihood on the first {n_s} rows of the same synthetic set, theta_B, "
+                      f"{best:.2f} s, LL={ll:.6f}; host has {os.cpu_count()} cores, reference is single-threaded"}
+
+
+def run_reference_arm(a):
+    """--impl reference: the reference's own CPU implementation, bounded sample per step."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from cugp_b200.loaders import synthetic_sine
+    from oracle import oracle
+    impl = oracle.reference() or oracle.port()
+    n_s = {"c5": 1536, "c3": 1536, "c2": 1024, "c4": 1500}[a.workload]
+    X, y = synthetic_sine(n_s + 64, 10)
+    Xt, X, y = X[n_s:], X[:n_s], y[:n_s]
+
+    def step():
+        if a.workload in ("c5", "c3"):
+            impl.loglik(X, y, TH_B)
+        elif a.workload == "c2":
+            impl.loglik(X, y, TH_B)
+            impl.grad(X, y, TH_B)
+        else:
+            impl.predict(X, y, TH_C, Xt)
+
+    for _ in range(a.warmup):
+        step()
+    t = time.perf_counter()
+    for _ in range(a.steps):
+        step()
+    ms = (time.perf_counter() - t) * 1e3 / a.steps
+    if a.workload in ("c5", "c3"):
+        metric, unit, value = "fp64_cholesky_tflops", "TFLOP/s", (n_s ** 3 / 3) / (ms * 1e-3) / 1e12
+        sample = f"compute_loglikelihood, n={n_s} synthetic rows (of {a.n}), theta_B"
+    elif a.workload == "c2":
+        metric, unit, value = "loglik_grad_evals_per_s", "evals/s", 1e3 / ms
+        sample = f"compute_loglikelihood + compute_gradient_loghyperparam, n={n_s} (of 4096), theta_B"
+    else:
+        metric, unit, value = "bcm_pred_pts_per_s", "pts/s", 64 / (ms * 1e-3)
+        sample = f"one expert (n={n_s}) predicting 64 points incl. its factorisation, theta_C"
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": a.workload, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": 1, "kind": impl.kind, "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+def fp64_probes(lib):
+    dm, df, cp = C.c_double(), C.c_double(), C.c_double()
+    lib.cugp_probe_fp64_peak(400.0, C.byref(dm), C.byref(df))
+    lib.cugp_probe_copy(1 << 30, 10, C.byref(cp))
+    return dm.value, df.value, cp.value
+
+
+def extra_c2(cg, torch, flush, n=4096, evals=6):
+    """loglik+grad evals/s on the C2 shape (synthetic rows, theta perturbed per evaluation)."""
+    from cugp_b200.loaders import synthetic_sine
+    X, y = synthetic_sine(n, 10, lo=-20.0, hi=20.0, noise=0.05)
+    g = cg.Covsum(n, 10)
+    g.set_data(X, y)
+    ts = []
+    for i in range(evals + 2):
+        g.set_loghyperparam([TH_B[0] + 1e-7 * i, TH_B[1], TH_B[2]])
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        g.loglik_resident()
+        g.grad_resident()
+        ts.append(time.perf_counter() - t)
+        flush()
+    g.close()
+    return 1.0 / statistics.median(ts[2:])
+
+
+def extra_c4(cg, torch, flush, m=10000):
+    """BCM 16 x 1500 prediction pts/s on this GPU alone (factorised experts resident; theta_C)."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "data_si24000.npz"))
+    from cugp_b200.loaders import synthetic_sine
+    Xt, _ = synthetic_sine(m, 10, seed=7)
+    b = cg.BCM(d["X"], d["y"], K=16, rank=0, world=1)
+    b.set_BCM_log_hyperparam(TH_C)
+    b.loglik_and_gradient()
+    ts = []
+    for _ in range(4):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        b.compute_BCM_test_means_and_var(Xt)
+        ts.append(time.perf_counter() - t)
+        flush()
+    b.close()
+    return m / statistics.median(ts[1:])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c2", "c4"])
+    ap.add_argument("--n", type=int, default=None, help="override the row count of the workload")
+    ap.add_argument("--m", type=int, default=10000, help="test points (c3/c4)")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-extra", action="store_true")
+    a = ap.parse_args()
+    a.n = a.n or {"c5": 100000, "c3": 10000, "c2": 4096, "c4": 24000}[a.workload]
+    a.warmup = max(a.warmup, 3) if a.impl == "native" else a.warmup
+    if a.impl == "reference":
+        return run_reference_arm(a)
+
+    rank, world, local, torch, dist = dist_setup(a.gpus)
+    import cugp_b200 as cg
+    from cugp_b200._lib import check, lib, ptr
+    from cugp_b200.loaders import synthetic_sine
+    L = lib()
+    check(L.cugp_set_device(local))
+    pk, pk_src = peaks()
+    flush = make_flush(torch)
+    sampler = ClockSampler(local)
+    n = a.n
+    out = {}
+    step_i = [0]
+
+    if a.workload in ("c5", "c3", "c2"):
+        lohi = (-20.0, 20.0, 0.05) if a.workload == "c2" else (-10.0, 10.0, 0.1)
+        X, y = synthetic_sine(n + a.m, 10, lo=lohi[0], hi=lohi[1], noise=lohi[2])   # rng seed 15618
+        Xt, X, y = X[n:], np.ascontiguousarray(X[:n]), np.ascontiguousarray(y[:n])
+        g = cg.Covsum(n, 10)
+        g.set_data(X, y)
+
+        def theta_i():
+            step_i[0] += 1
+            return [TH_B[0] + 1e-7 * step_i[0], TH_B[1], TH_B[2]]     # new theta: nothing cached is reused
+
+        if a.workload == "c2":
+            def step():
+                g.set_loghyperparam(theta_i())
+                g.loglik_resident()
+                g.grad_resident()
+
+            def step_e2e():
+                g.set_loghyperparam(theta_i())
+                g.compute_loglikelihood(X, y)
+                g.compute_gradient_loghyperparam(X, y)
+            d2h = 8 + 24
+        elif a.workload == "c3":
+            def step():
+                g.set_loghyperparam(theta_i())
+                g.loglik_resident()
+                g.compute_test_means_and_variances(X, y, Xt)
+
+            step_e2e = step
+            d2h = 8 + 16 * a.m
+        else:
+            def step():
+                g.set_loghyperparam(theta_i())
+                g.loglik_resident()
+
+            def step_e2e():
+                g.set_loghyperparam(theta_i())
+                g.compute_loglikelihood(X, y)
+            d2h = 8
+        h2d = X.nbytes + y.nbytes + (Xt.nbytes if a.workload == "c3" else 0)
+        use_flush = flush if a.workload == "c2" else None
+
+        g.profile(True)
+        sampler.start()
+        L.cugp_launch_count_reset()
+        ms, wall_ms = timed_steps(torch, dist, step, a.steps, a.warmup, use_flush)
+        launches = L.cugp_launch_count()
+        clocks = sampler.stop()
+        # dominant kernel (SYRK trailing update): launches of the LAST (warmup + steps) passes were bracketed
+        syrk_ms, syrk_flops, syrk_cnt = g.profile_read()
+        g.profile(False)
+        ms_e2e, _ = timed_steps(torch, dist, step_e2e, 1 if n >= 50000 else max(1, min(a.steps, 3)), 0, use_flush)
+
+        if a.workload == "c2":
+            metric, unit, per_rank, per_rank_e2e = "loglik_grad_evals_per_s", "evals/s", 1e3 / ms, 1e3 / ms_e2e
+        else:
+            metric, unit = "fp64_cholesky_tflops", "TFLOP/s"
+            per_rank, per_rank_e2e = (n ** 3 / 3) / (ms * 1e-3) / 1e12, (n ** 3 / 3) / (ms_e2e * 1e-3) / 1e12
+        out.update(metric=metric, unit=unit, value=per_rank * world, ms_per_step=ms, scaling="weak",
+                   e2e={"value": per_rank_e2e * world, "unit": unit, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h)},
+                   gpu_launches=int(launches * a.steps / (a.steps + a.warmup)))
+        # factorisation alone (events inside the library), for the record
+        g.set_loghyperparam(theta_i())
+        ms_cov, ms_chol = g.factorize_resident()
+        out["phases_ms"] = {"covariance": ms_cov, "cholesky": ms_chol, "cholesky_tflops": (n ** 3 / 3) / (ms_chol * 1e-3) / 1e12}
+        config = {"workload": {"c5": f"C5 synthetic exact GP n={n} d=10: covariance build + blocked Cholesky + solves + LL",
+                               "c3": f"C3 exact GP n={n} d=10 train + predict {a.m} points",
+                               "c2": f"C2 exact GP n={n} d=10 hyper-parameter loop: LL + gradient per evaluation"}[a.workload],
+                  "n": n, "d": 10, "theta": TH_B, "parallelism": f"replicas x{world} (exact GP does not shard)",
+                  "l2": "256 MB flush between steps" if use_flush else "inputs (8 n^2 B) exceed L2"}
+        g.close()
+        del g
+    else:  # c4: BCM, experts sharded over ranks, NCCL allreduce of the moments
+        d = np.load(os.path.join(ROOT, "tests", "golden", "data_si24000.npz"))
+        Xt, _ = synthetic_sine(a.m, 10, seed=7)
+        b = cg.BCM(d["X"], d["y"], K=16)
+
+        def step():
+            step_i[0] += 1
+            b.set_BCM_log_hyperparam([TH_C[0] + 1e-7 * step_i[0], TH_C[1], TH_C[2]])
+            b.loglik_and_gradient()
+            b.compute_BCM_test_means_and_var(Xt)
+
+        sampler.start()
+        L.cugp_launch_count_reset()
+        ms, wall_ms = timed_steps(torch, dist, step, a.steps, a.warmup, flush)
+        launches = L.cugp_launch_count()
+        clocks = sampler.stop()
+        syrk_ms = syrk_flops = syrk_cnt = 0
+        out.update(metric="bcm_pred_pts_per_s", unit="pts/s", value=a.m / (ms * 1e-3), ms_per_step=ms, scaling="strong",
+                   e2e={"value": a.m / (ms * 1e-3), "unit": "pts/s", "h2d_bytes_per_step": int(Xt.nbytes),
+                        "d2h_bytes_per_step": int(16 * a.m + 32)},
+                   gpu_launches=int(launches * a.steps / (a.steps + a.warmup)))
+        config = {"workload": f"C4 BCM si24000 16 experts x 1500, theta_C: LL+gradient eval then predict {a.m} points per step",
+                  "n": 24000, "d": 10, "experts": 16, "parallelism": f"experts e%{world} per rank, allreduce(4) + allreduce(2m)",
+                  "l2": "256 MB flush between steps"}
+        b.close()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    dmma, dfma, copy_gbs = fp64_probes(L)
+    # cuBLAS DGEMM as a library ceiling for context only (never on the product path)
+    try:
+        A = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+        torch.matmul(A, A)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(3):
+            torch.matmul(A, A)
+        torch.cuda.synchronize()
+        cublas = 3 * 2 * 8192 ** 3 / (time.perf_counter() - t) / 1e12
+        del A
+    except Exception:
+        cublas = None
+    if syrk_cnt:
+        achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
+        out["roofline"] = {"bound": "tensor", "kernel": "dgemm_dmma_kernel (SYRK trailing update A22 -= L21 L21^T, lower tiles)",
+                           "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma, "traffic": None,
+                           "peak_source": "measured here: register-resident mma.sync.m8n8k4.f64 loop (cugp_probe_fp64_peak); "
+                                          "MEASURED_PEAKS.json has no FP64 entry",
+                           "frac_of_dfma_measured": achieved / dfma, "frac_of_nominal_37": achieved / NOMINAL_FP64_TFLOPS,
+                           "launches_timed": syrk_cnt, "share_of_step": syrk_ms / ((a.steps + a.warmup) * ms),
+                           "algorithmic_flops_per_launch": "m(m+1)*128 for an m x m trailing block"}
+    out["fp64_peaks_tflops"] = {"dmma_probe": dmma, "dfma_probe": dfma, "cublas_dgemm_8192": cublas, "nominal": NOMINAL_FP64_TFLOPS}
+    out["hbm"] = {"copy_probe_gbs": copy_gbs, "peak_gbs": pk.get("hbm_gbs"), "peak_source": pk_src}
+    if not a.no_extra and a.workload == "c5":
+        try:
+            out["extra"] = {"c2_loglik_grad_evals_per_s": extra_c2(cg, torch, flush),
+                            "c4_bcm_pred_pts_per_s_1gpu": extra_c4(cg, torch, flush)}
+        except Exception as e:  # the headline must still print
+            out["extra"] = {"error": repr(e)}
+    n_s = 2048 if a.workload in ("c5", "c3") else 1024
+    cpu = cpu_baseline("reference", n_s, TH_B)
+    if a.workload == "c2":
+        from oracle import oracle
+        impl = oracle.reference() or oracle.port()
+        Xs, ys = synthetic_sine(n_s, 10, lo=-20.0, hi=20.0, noise=0.05)
+        t = time.perf_counter()
+        impl.loglik(Xs, ys, TH_B)
+        impl.grad(Xs, ys, TH_B)
+        dt = time.perf_counter() - t
+        cpu = {"value": 1.0 / dt, "unit": "evals/s", "cores": 1, "kind": impl.kind,
+               "sample": f"one LL + gradient at n={n_s} (of {n}), theta_B, {dt:.1f} s"}
+    elif a.workload == "c4":
+        cpu = {"value": None, "unit": "pts/s", "cores": 1, "kind": "reference",
+               "sample": "see BASELINE.md: BCM 16x1500 predict(8 pts) 172 s on one core"}
+    line = {"metric": out.pop("metric"), "value": out.pop("value"), "unit": out.pop("unit"), "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": out.pop("ms_per_step"), "higher_is_better": True, "scaling": out.pop("scaling"),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": out.pop("e2e"), "gpu_launches": out.pop("gpu_launches"), "cpu_baseline": cpu}
+    line.update(out)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,16 @@ class Covsum:
         return a.value, b.value
 
 
+    def profile(self, enable: bool = True):
+        check(lib().cugp_covsum_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """(summed SYRK launch ms, their algorithmic flops, launch count) since profile(True)."""
+        ms, fl, cnt = C.c_double(), C.c_double(), C.c_long()
+        check(lib().cugp_covsum_profile_read(self._h, C.byref(ms), C.byref(fl), C.byref(cnt)))
+        return ms.value, fl.value, cnt.value
+
+
 # ---- matrixops (common/matrixops.h:5-25) ---------------------------------------------------------------------
 def get_cholesky(A):
     """matrixops.cpp:68-108: dense L with zeroed upper triangle; NaN (no exception) on a negative pivot."""

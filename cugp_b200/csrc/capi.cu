@@ -300,6 +300,22 @@ int cugp_covsum_factorize_resident(cugp_covsum* h, float* ms_cov, float* ms_chol
     CUGP_CATCH
 }
 
+int cugp_covsum_profile(cugp_covsum* h, int enable) {
+    CUGP_TRY
+    if (!h) return CUGP_ERR_INVALID;
+    h->gp->prof.on = enable != 0;
+    h->gp->prof_begin();
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_covsum_profile_read(cugp_covsum* h, double* syrk_ms, double* syrk_flops, long* launches) {
+    CUGP_TRY
+    if (!h) return CUGP_ERR_INVALID;
+    h->gp->prof_collect(syrk_ms, syrk_flops, launches);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+
 static int covsum_eval(void* ctx, const double theta[3], double* f, double g[3]) {
     cugp_covsum* h = static_cast<cugp_covsum*>(ctx);
     try {

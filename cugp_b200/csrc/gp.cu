@@ -26,8 +26,18 @@ void dfree(T*& p) {
 // ------------------------------------------------------------------------------------------------
 // blocked factorisations built from the DMMA GEMM and the diagonal-block kernel
 // ------------------------------------------------------------------------------------------------
+static cudaEvent_t prof_event(GpBatch::Prof* prof) {
+    if (prof->used == prof->ev.size()) {
+        cudaEvent_t e;
+        CUGP_CUDA(cudaEventCreate(&e));
+        prof->ev.push_back(e);
+    }
+    return prof->ev[prof->used++];
+}
+
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part, int batch,
-                   cudaStream_t st, long* launches) {
+                   cudaStream_t st, long* launches, GpBatch::Prof* prof) {
+    if (prof && !prof->on) prof = nullptr;
     const int nblk = cdiv(n, kDiag);
     for (int blk = 0; blk < nblk; blk++) {
         const int j0 = blk * kDiag;
@@ -54,7 +64,13 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
         q.alpha = -1.0; q.beta = 1.0;
         q.batch = batch;
         q.lower_tiles = 1;
+        if (prof) CUGP_CUDA(cudaEventRecord(prof_event(prof), st));
         launch_gemm(q, true, true, pick_config(m, m, batch, true), st);
+        if (prof) {
+            CUGP_CUDA(cudaEventRecord(prof_event(prof), st));
+            prof->flops += (double)batch * (double)m * ((double)m + 1.0) * (double)kDiag;  // lower triangle, 2 flop per MAC
+            prof->count++;
+        }
         if (launches) *launches += 2;
     }
 }
@@ -145,6 +161,7 @@ GpBatch::~GpBatch() {
     dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout);
     dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar);
     if (hstage) cudaFreeHost(hstage);
+    for (cudaEvent_t e : prof.ev) cudaEventDestroy(e);
     if (own_stream && st) cudaStreamDestroy(st);
 }
 
@@ -193,7 +210,26 @@ void GpBatch::build_K(int full) {
 }
 
 void GpBatch::potrf() {
-    potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches);
+    potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof);
+}
+
+void GpBatch::prof_begin() {
+    prof.used = 0;
+    prof.flops = 0.0;
+    prof.count = 0;
+}
+
+void GpBatch::prof_collect(double* ms, double* flops, long* count) {
+    sync();
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < prof.used; i += 2) {
+        float t = 0.f;
+        CUGP_CUDA(cudaEventElapsedTime(&t, prof.ev[i], prof.ev[i + 1]));
+        total += t;
+    }
+    if (ms) *ms = total;
+    if (flops) *flops = prof.flops;
+    if (count) *count = prof.count;
 }
 
 void GpBatch::factorize() {

@@ -7,6 +7,8 @@
 #include "gemm_dmma.cuh"
 #include "kernels.cuh"
 
+#include <vector>
+
 namespace cugp {
 
 struct GpBatch {
@@ -35,6 +37,16 @@ struct GpBatch {
     Hyper h{};
     bool have_data = false, have_L = false, have_alpha = false, have_T = false, have_Kinv = false;
     long launches = 0;  // kernels launched since the last reset (bench.py `gpu_launches`)
+    // optional timing of the dominant kernel (SYRK trailing update) with CUDA events on the launching stream
+    struct Prof {
+        bool on = false;
+        std::vector<cudaEvent_t> ev;   // pairs (start, stop)
+        size_t used = 0;
+        double flops = 0.0;            // algorithmic flops of the bracketed launches
+        long count = 0;
+    } prof;
+    void prof_begin();                     // reset counters (events are reused)
+    void prof_collect(double* ms, double* flops, long* count);
 
     GpBatch(int B, int n, int d, cudaStream_t stream = nullptr);
     ~GpBatch();
@@ -68,7 +80,7 @@ struct GpBatch {
 // Blocked right-looking Cholesky of `batch` matrices in place (lower), with the inverses of the
 // 128x128 diagonal blocks and per-block log-determinant partials as by-products.
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part,
-                   int batch, cudaStream_t st, long* launches);
+                   int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr);
 // T = L^-1 by recursive doubling over 128-blocks (W is n x n scratch).
 void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t sM, int n, const double* invd,
                      int64_t sInvd, int batch, cudaStream_t st, long* launches);

@@ -522,7 +522,9 @@ __global__ void __launch_bounds__(256)
         double quad = red[0];
         scal[b * 4 + 0] = quad;
         scal[b * 4 + 1] = ld;
-        scal[b * 4 + 2] = -0.5 * (quad + ld + n * 1.83787);  // covkernel.cpp:127 (truncated log 2pi)
+        // covkernel.cpp:127: -0.5 * (first + second + n * 1.83787), truncated log(2 pi); no FMA contraction so the
+        // scalar arithmetic is the reference's to the last bit
+        scal[b * 4 + 2] = -0.5 * __dadd_rn(__dadd_rn(quad, ld), __dmul_rn((double)n, 1.83787));
         scal[b * 4 + 3] = 0.0;
     }
 }

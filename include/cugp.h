@@ -101,6 +101,12 @@ int cugp_covsum_alpha_resident(cugp_covsum *h, double *alpha);
  * (CUDA events on the launching stream), for the FP64 roofline (n^3/3 flop). */
 int cugp_covsum_factorize_resident(cugp_covsum *h, float *ms_cov, float *ms_chol);
 
+/* Dominant-kernel timing for the roofline: with profiling enabled every SYRK trailing-update launch of the
+ * Cholesky is bracketed by CUDA events on its stream.  profile_read returns, since the last profile(h, 1):
+ * the summed launch duration (ms), their algorithmic flops (sum of m(m+1)*128 per launch) and the count. */
+int cugp_covsum_profile(cugp_covsum *h, int enable);
+int cugp_covsum_profile_read(cugp_covsum *h, double *syrk_ms, double *syrk_flops, long *launches);
+
 /* ---- matrixops (common/matrixops.h:5-25) ------------------------------------------------------------ */
 /* get_cholesky, matrixops.cpp:68-108: L dense n x n with zeroed upper triangle; NaN on a negative pivot. */
 int cugp_cholesky(const double *A, double *L, int n);
