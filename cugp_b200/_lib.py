@@ -31,6 +31,7 @@ SIGNATURES = {
     "cugp_set_device": (C.c_int, [C.c_int]),
     "cugp_launch_count": (C.c_long, []),
     "cugp_launch_count_reset": (None, []),
+    "cugp_set_tuning": (C.c_int, [C.c_char_p, C.c_long]),
     "cugp_covsum_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "cugp_covsum_destroy": (C.c_int, [C.c_void_p]),
     "cugp_covsum_set_loghyper": (C.c_int, [C.c_void_p, dp]),
@@ -69,6 +70,7 @@ SIGNATURES = {
     "cugp_poe_finalize": (C.c_int, [dp, C.c_int, dp, dp]),
     "cugp_bcm_predict": (C.c_int, [C.c_void_p, dp, C.c_int, dp, dp]),
     "cugp_probe_fp64_peak": (C.c_int, [C.c_float, dp, dp]),
+    "cugp_probe_dmma": (C.c_int, [C.c_float, dp, dp]),
     "cugp_probe_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, dp]),
     "cugp_debug_gemm": (C.c_int, [dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                   C.c_int, C.c_int, dp]),

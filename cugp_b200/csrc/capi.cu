@@ -16,6 +16,7 @@
 namespace cugp {
 void probe_fp64_peak(float target_ms, double* dmma_tflops, double* dfma_tflops);
 void probe_gemm(int M, int N, int K, int iters, double* tflops);
+void probe_dmma(float target_ms, double* tflops, double* sm_mhz);
 void probe_copy(size_t bytes, int iters, double* gbs);
 
 static thread_local char g_err[512] = "";
@@ -125,6 +126,24 @@ long cugp_launch_count(void) {
 void cugp_launch_count_reset(void) {
     g_launch_base = 0;
     for (GpBatch* g : live_batches()) g->launches = 0;
+}
+
+int cugp_set_tuning(const char* key, long value) {
+    if (!key) return CUGP_ERR_INVALID;
+    if (std::strcmp(key, "potrf_nb") == 0) {
+        if (value != 0 && (value < kDiag || value % kDiag)) {
+            set_last_error("potrf_nb must be 0 (auto) or a multiple of %d", kDiag);
+            return CUGP_ERR_INVALID;
+        }
+        set_potrf_outer_width((int)value);
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "diag_kernel") == 0) {
+        set_diag_variant(value != 0);
+        return CUGP_OK;
+    }
+    set_last_error("unknown tuning key '%s'", key);
+    return CUGP_ERR_INVALID;
 }
 
 // ---- Covsum -----------------------------------------------------------------------------------------
@@ -627,6 +646,14 @@ int cugp_probe_fp64_peak(float ms, double* dmma_tflops, double* dfma_tflops) {
     probe_fp64_peak(ms, &a, &b);
     if (dmma_tflops) *dmma_tflops = a;
     if (dfma_tflops) *dfma_tflops = b;
+    return CUGP_OK;
+    CUGP_CATCH
+}
+int cugp_probe_dmma(float ms, double* tflops, double* sm_mhz) {
+    CUGP_TRY
+    if (int rc = require_device()) return rc;
+    if (!tflops || !sm_mhz || ms <= 0.f) return CUGP_ERR_INVALID;
+    probe_dmma(ms, tflops, sm_mhz);
     return CUGP_OK;
     CUGP_CATCH
 }

@@ -77,12 +77,21 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) dgemm_dmma_kernel(co
 
     int ti, tj;
     if (p.lower_tiles) {
-        // linear index over the lower-triangular tile set, row by row
+        // linear index over the tiles with ti >= tj of an M x N (M >= N) lower trapezoid: first the
+        // triangle of the top N x N square row by row, then the full-width tile rows below it
+        const int tn = (p.N + BN - 1) / BN;
+        const int tri = tn * (tn + 1) / 2;
         int x = blockIdx.x;
-        ti = (int)((sqrt(8.0 * (double)x + 1.0) - 1.0) * 0.5);
-        while ((int64_t)(ti + 1) * (ti + 2) / 2 <= x) ti++;
-        while ((int64_t)ti * (ti + 1) / 2 > x) ti--;
-        tj = x - (int)((int64_t)ti * (ti + 1) / 2);
+        if (x < tri) {
+            ti = (int)((sqrt(8.0 * (double)x + 1.0) - 1.0) * 0.5);
+            while ((int64_t)(ti + 1) * (ti + 2) / 2 <= x) ti++;
+            while ((int64_t)ti * (ti + 1) / 2 > x) ti--;
+            tj = x - (int)((int64_t)ti * (ti + 1) / 2);
+        } else {
+            x -= tri;
+            ti = tn + x / tn;
+            tj = x % tn;
+        }
     } else {
         int tiles_n = (p.N + BN - 1) / BN;
         ti = blockIdx.x / tiles_n;
@@ -239,7 +248,11 @@ void launch_one(const GemmParams& p, cudaStream_t stream) {
         configured = true;
     }
     int tiles_m = cdiv(p.M, BM), tiles_n = cdiv(p.N, BN);
-    int64_t tiles = p.lower_tiles ? (int64_t)tiles_m * (tiles_m + 1) / 2 : (int64_t)tiles_m * tiles_n;
+    int64_t tiles = (int64_t)tiles_m * tiles_n;
+    if (p.lower_tiles) {  // trapezoid: needs M >= N and square tiles
+        if (BM != BN || tiles_m < tiles_n) throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};
+        tiles = (int64_t)tiles_n * (tiles_n + 1) / 2 + (int64_t)(tiles_m - tiles_n) * tiles_n;
+    }
     if (tiles <= 0 || p.batch <= 0) return;
     dim3 grid((unsigned)tiles, (unsigned)p.batch);
     kern<<<grid, NT, smem, stream>>>(p);
@@ -260,7 +273,7 @@ int gemm_tile_m(GemmConfig cfg) { return cfg == GEMM_BIG ? 128 : 64; }
 
 GemmConfig pick_config(int M, int N, int batch, bool lower_tiles) {
     int64_t tm = cdiv(M, 128), tn = cdiv(N, 128);
-    int64_t tiles = (lower_tiles ? tm * (tm + 1) / 2 : tm * tn) * batch;
+    int64_t tiles = (lower_tiles ? tn * (tn + 1) / 2 + (tm - tn) * tn : tm * tn) * batch;
     return tiles >= 2 * 148 ? GEMM_BIG : GEMM_SMALL;
 }
 

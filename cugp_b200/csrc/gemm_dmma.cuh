@@ -26,7 +26,7 @@ struct GemmParams {
     int batch;               // total batch count = batch_inner * outer
     int batch_inner;         // 0/1: single level.  >1: index b -> (b % inner) * s? + (b / inner) * s?2
     int64_t sA2, sB2, sC2;   // outer batch strides (used when batch_inner > 1)
-    int lower_tiles;         // 1: only output tiles with ti >= tj are computed (needs BM == BN)
+    int lower_tiles;         // 1: only output tiles with ti >= tj are computed (needs BM == BN and M >= N: lower trapezoid)
     int klo_ti, klo_tj;      // restrict k >= ti*BM / k >= tj*BN   (triangular operand structure)
     int khi_ti, khi_tj;      // restrict k <  (ti+1)*BM / (tj+1)*BN
     double* colsumsq;        // non-null: write per-row-tile column sums of squares [tiles_m][N] instead of C

@@ -2,6 +2,7 @@
 #include "gp.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -35,32 +36,72 @@ static cudaEvent_t prof_event(GpBatch::Prof* prof) {
     return prof->ev[prof->used++];
 }
 
+// Outer block width of the two-level factorisation: the trailing update runs with K = outer width, so its
+// C tiles are read and written once per outer step instead of once per 128 columns (the K = 128 update is
+// bound by that traffic: 8 flop/B).  Small matrices keep narrow outer blocks so the update still fills the GPU.
+static int g_potrf_nb = 0;  // 0: by size; otherwise forced (cugp_set_tuning("potrf_nb", v) or CUGP_POTRF_NB)
+void set_potrf_outer_width(int nb) { g_potrf_nb = nb; }
+int potrf_outer_width(int n) {
+    static const int env = [] {
+        const char* e = std::getenv("CUGP_POTRF_NB");
+        return e ? std::atoi(e) : 0;
+    }();
+    const int forced = g_potrf_nb ? g_potrf_nb : env;
+    if (forced >= kDiag) return forced / kDiag * kDiag;
+    if (n >= 24576) return 1024;
+    if (n >= 6144) return 512;
+    if (n >= 3072) return 256;
+    return kDiag;
+}
+
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part, int batch,
                    cudaStream_t st, long* launches, GpBatch::Prof* prof) {
     if (prof && !prof->on) prof = nullptr;
     const int nblk = cdiv(n, kDiag);
-    for (int blk = 0; blk < nblk; blk++) {
-        const int j0 = blk * kDiag;
-        launch_potrf_diag(A, ld, sA, n, j0, invd, sInvd, logdet_part, nblk, blk, batch, st);
-        if (launches) ++*launches;
-        const int m = n - (j0 + kDiag);
-        if (m <= 0) break;
-        double* A21 = A + (int64_t)(j0 + kDiag) * ld + j0;
-        // TRSM panel: L21 = A21 * inv(L11)^T, in place (each CTA owns whole rows of the panel).
-        GemmParams p{};
-        p.A = A21; p.lda = ld; p.sA = sA;
-        p.B = invd + (int64_t)blk * kDiag * kDiag; p.ldb = kDiag; p.sB = sInvd;
-        p.C = A21; p.ldc = ld; p.sC = sA;
-        p.M = m; p.N = kDiag; p.K = kDiag;
-        p.alpha = 1.0; p.beta = 0.0;
-        p.batch = batch;
-        launch_gemm(p, true, true, GEMM_TALL, st);
-        // SYRK trailing update: A22 -= L21 L21^T, lower tiles only.
+    const int NB = potrf_outer_width(n);
+    for (int J0 = 0; J0 < n; J0 += NB) {
+        const int Jend = std::min(n, J0 + NB);
+        // ---- panel: right-looking over the 128-column blocks of [J0, Jend), full height, updates confined to the panel
+        for (int j0 = J0; j0 < Jend; j0 += kDiag) {
+            const int blk = j0 / kDiag;
+            launch_potrf_diag(A, ld, sA, n, j0, invd, sInvd, logdet_part, nblk, blk, batch, st);
+            if (launches) ++*launches;
+            const int r0 = j0 + kDiag;
+            const int m = n - r0;
+            if (m <= 0) break;
+            double* A21 = A + (int64_t)r0 * ld + j0;
+            // TRSM panel: L21 = A21 * inv(L11)^T, in place (each CTA owns whole rows of the panel).
+            GemmParams p{};
+            p.A = A21; p.lda = ld; p.sA = sA;
+            p.B = invd + (int64_t)blk * kDiag * kDiag; p.ldb = kDiag; p.sB = sInvd;
+            p.C = A21; p.ldc = ld; p.sC = sA;
+            p.M = m; p.N = kDiag; p.K = kDiag;
+            p.alpha = 1.0; p.beta = 0.0;
+            p.batch = batch;
+            launch_gemm(p, true, true, GEMM_TALL, st);
+            if (launches) ++*launches;
+            // remaining columns of the panel: A[r0:, r0:Jend] -= L21 L21[0:w]^T, lower trapezoid
+            const int w = Jend - r0;
+            if (w <= 0) continue;
+            GemmParams q{};
+            q.A = A21; q.lda = ld; q.sA = sA;
+            q.B = A21; q.ldb = ld; q.sB = sA;
+            q.C = A + (int64_t)r0 * (ld + 1); q.ldc = ld; q.sC = sA;
+            q.M = m; q.N = w; q.K = kDiag;
+            q.alpha = -1.0; q.beta = 1.0;
+            q.batch = batch;
+            q.lower_tiles = 1;
+            launch_gemm(q, true, true, pick_config(m, w, batch, true), st);
+            if (launches) ++*launches;
+        }
+        // ---- trailing update: A[Jend:, Jend:] -= P P^T with P = L[Jend:, J0:Jend], lower tiles, K = outer width
+        const int m = n - Jend;
+        if (m <= 0) continue;
         GemmParams q{};
-        q.A = A21; q.lda = ld; q.sA = sA;
-        q.B = A21; q.ldb = ld; q.sB = sA;
-        q.C = A + (int64_t)(j0 + kDiag) * (ld + 1); q.ldc = ld; q.sC = sA;
-        q.M = m; q.N = m; q.K = kDiag;
+        q.A = A + (int64_t)Jend * ld + J0; q.lda = ld; q.sA = sA;
+        q.B = q.A; q.ldb = ld; q.sB = sA;
+        q.C = A + (int64_t)Jend * (ld + 1); q.ldc = ld; q.sC = sA;
+        q.M = m; q.N = m; q.K = Jend - J0;
         q.alpha = -1.0; q.beta = 1.0;
         q.batch = batch;
         q.lower_tiles = 1;
@@ -68,10 +109,10 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
         launch_gemm(q, true, true, pick_config(m, m, batch, true), st);
         if (prof) {
             CUGP_CUDA(cudaEventRecord(prof_event(prof), st));
-            prof->flops += (double)batch * (double)m * ((double)m + 1.0) * (double)kDiag;  // lower triangle, 2 flop per MAC
+            prof->flops += (double)batch * (double)m * ((double)m + 1.0) * (double)(Jend - J0);  // lower triangle, 2 flop per MAC
             prof->count++;
         }
-        if (launches) *launches += 2;
+        if (launches) ++*launches;
     }
 }
 

@@ -81,6 +81,9 @@ struct GpBatch {
 // 128x128 diagonal blocks and per-block log-determinant partials as by-products.
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part,
                    int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr);
+// Outer block width used for an n x n factorisation; set_potrf_outer_width(0) restores the size-based default.
+int potrf_outer_width(int n);
+void set_potrf_outer_width(int nb);
 // T = L^-1 by recursive doubling over 128-blocks (W is n x n scratch).
 void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t sM, int n, const double* invd,
                      int64_t sInvd, int batch, cudaStream_t st, long* launches);

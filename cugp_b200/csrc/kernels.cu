@@ -388,6 +388,214 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2a, blocked version: the 128x128 block is processed in four 32-column panels so the serial chain is
+// 128 short warp-level column steps (registers + one shared broadcast per column) instead of 256
+// CTA-wide barriers, and everything quadratic in the panel (SYRK inside the block, the off-diagonal
+// blocks of the inverse) runs on DMMA over 8x8 output blocks spread across the 16 warps.
+//   L(i,j) = S[i][j] (j <= i);   T(i,j) = inv(L)(i,j) = S[j][i+1] (j <= i)   -- same packing as above.
+// ------------------------------------------------------------------------------------------------
+constexpr int SB = 32;                 // panel width inside the diagonal block
+constexpr int TLD = 65;                // row stride of the 64x64 scratch of the inverse recursion
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// C(i,j) = sum_k A(i,k) B(k,j) over 8x8 output blocks, one block per warp at a time.  `lower`: only blocks
+// with bi >= bj of an mb x mb block grid.  krange(i0, j0, klo, khi) gives the k interval (multiples of 4).
+template <class FA, class FB, class FK, class FS>
+__device__ __forceinline__ void cta_gemm8(int mb, int nbk, bool lower, FA A, FB B, FK krange, FS store, int warp,
+                                          int nwarps, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    const int nblocks = lower ? mb * (mb + 1) / 2 : mb * nbk;
+    for (int x = warp; x < nblocks; x += nwarps) {
+        int bi, bj;
+        if (lower) {
+            bi = (int)((sqrtf(8.f * (float)x + 1.f) - 1.f) * 0.5f);
+            while ((bi + 1) * (bi + 2) / 2 <= x) bi++;
+            while (bi * (bi + 1) / 2 > x) bi--;
+            bj = x - bi * (bi + 1) / 2;
+        } else {
+            bi = x / nbk;
+            bj = x % nbk;
+        }
+        const int i0 = bi * 8, j0 = bj * 8;
+        int klo, khi;
+        krange(i0, j0, klo, khi);
+        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator chains
+        int k = klo;
+        for (; k + 8 <= khi; k += 8) {
+            dmma884(c0, c1, A(i0 + g, k + q), B(k + q, j0 + g));
+            dmma884(e0, e1, A(i0 + g, k + 4 + q), B(k + 4 + q, j0 + g));
+        }
+        if (k < khi) dmma884(c0, c1, A(i0 + g, k + q), B(k + q, j0 + g));
+        store(i0 + g, j0 + 2 * q, c0 + e0, c1 + e1);
+    }
+}
+
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
+    potrf_diag_blocked_kernel(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd,
+                              double* logdet_part, int nblk, int blk) {
+    extern __shared__ __align__(16) double S[];
+    double* tmp = S + DB * DLD;                // [64][TLD]
+    double* rdiag = tmp + 64 * TLD;            // [128] reciprocals of L's diagonal
+    double* colbuf = rdiag + DB;               // [2][32] broadcast buffer of the warp-level factorisation
+    double* red = colbuf + 2 * SB;             // [128]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = DIAG_THREADS / 32;
+    const int64_t b = blockIdx.x;
+    double* Ab = A + b * sA + (int64_t)j0 * ld + j0;
+    const int nb = min(DB, n - j0);
+
+    for (int e = tid; e < DB * DLD; e += DIAG_THREADS) {
+        int i = e / DLD, j = e % DLD;
+        double v = 0.0;
+        if (j <= i) {  // lower triangle of A, identity padded
+            if (i < nb) v = Ab[(int64_t)i * ld + j];
+            else if (i == j) v = 1.0;
+        }
+        S[e] = v;
+    }
+    __syncthreads();
+
+    // ---------------- Cholesky, panel by panel ----------------
+    for (int c0 = 0; c0 < DB; c0 += SB) {
+        if (warp == 0) {
+            // 32x32 diagonal sub-block: lane i owns row i in registers (matrixops.cpp:74-98 on the sub-block).
+            double a[SB];
+#pragma unroll
+            for (int c = 0; c < SB; c++) a[c] = (c <= lane) ? S[(c0 + lane) * DLD + c0 + c] : 0.0;
+#pragma unroll
+            for (int j = 0; j < SB; j++) {
+                const double ajj = __shfl_sync(0xffffffffu, a[j], j);
+                const double d = sqrt(ajj);          // negative pivot -> NaN, propagates (matrixops.cpp:77)
+                const double rd = 1.0 / d;
+                const double l = (lane == j) ? d : a[j] * rd;   // lanes < j hold 0
+                a[j] = l;
+                if (lane == j) rdiag[c0 + j] = rd;
+                if (j + 1 < SB) {
+                    if (lane == j + 1) a[j + 1] -= l * l;   // next pivot first: it does not wait for the broadcast
+                    double* cb = colbuf + (j & 1) * SB;
+                    cb[lane] = l;
+                    __syncwarp();
+#pragma unroll
+                    for (int c = j + 1; c < SB; c++) {
+                        const double lc = cb[c];     // L(c, j), broadcast
+                        if (c == j + 1) {
+                            if (lane != j + 1) a[c] -= l * lc;   // lane j+1 already applied l*l
+                        } else {
+                            a[c] -= l * lc;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < SB; c++)
+                if (c <= lane) S[(c0 + lane) * DLD + c0 + c] = a[c];
+        }
+        __syncthreads();
+        const int r0 = c0 + SB, m = DB - r0;
+        if (m <= 0) break;
+        // rows below: X L11^T = A21 by forward substitution, one thread per row (matrixops.cpp:330-340 transposed)
+        if (tid < m) {
+            const int r = r0 + tid;
+            double a[SB];
+#pragma unroll
+            for (int c = 0; c < SB; c++) a[c] = S[r * DLD + c0 + c];
+#pragma unroll
+            for (int c = 0; c < SB; c++) {
+                const double x = a[c] * rdiag[c0 + c];
+                a[c] = x;
+#pragma unroll
+                for (int k = c + 1; k < SB; k++) a[k] -= x * S[(c0 + k) * DLD + c0 + c];
+            }
+#pragma unroll
+            for (int c = 0; c < SB; c++) S[r * DLD + c0 + c] = a[c];
+        }
+        __syncthreads();
+        // trailing block of the diagonal block: A22 -= L21 L21^T (lower 8x8 blocks), K = 32
+        cta_gemm8(
+            m / 8, m / 8, true, [&](int i, int k) { return S[(r0 + i) * DLD + c0 + k]; },
+            [&](int k, int j) { return S[(r0 + j) * DLD + c0 + k]; },
+            [&](int, int, int& klo, int& khi) { klo = 0; khi = SB; },
+            [&](int i, int j, double v0, double v1) {
+                double* dst = S + (r0 + i) * DLD + r0 + j;
+                if (j <= i) dst[0] -= v0;
+                if (j + 1 <= i) dst[1] -= v1;
+            },
+            warp, NW, lane);
+        __syncthreads();
+    }
+
+    // ---------------- inverse ----------------
+    // diagonal 32x32 blocks: lane c solves L x = e_c (matrixops.cpp:330-340), 4 warps = 4 blocks
+    if (warp < DB / SB) {
+        const int c0 = warp * SB;
+        double r[SB];
+#pragma unroll
+        for (int i = 0; i < SB; i++) r[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < SB; k++) {
+            const double x = r[k] * rdiag[c0 + k];
+            r[k] = x;
+#pragma unroll
+            for (int i = k + 1; i < SB; i++) r[i] -= S[(c0 + i) * DLD + c0 + k] * x;
+        }
+#pragma unroll
+        for (int k = 0; k < SB; k++)
+            if (k >= lane) S[(c0 + lane) * DLD + c0 + k + 1] = r[k];  // T(c0+k, c0+lane)
+    }
+    __syncthreads();
+    // off-diagonal blocks by doubling: T21 = -T22 (L21 T11)
+    for (int h = SB; h < DB; h *= 2) {
+        const int npairs = DB / (2 * h);
+        const int hb = h / 8;
+        for (int pr = 0; pr < npairs; pr++) {   // pairs are processed one after the other (tmp is one buffer)
+            const int r1 = pr * 2 * h, r2 = r1 + h;
+            // tmp = L21 T11 : k in [j0 rounded down to 4, h)  (T11 lower triangular)
+            cta_gemm8(
+                hb, hb, false, [&](int i, int k) { return S[(r2 + i) * DLD + r1 + k]; },
+                [&](int k, int j) { return k >= j ? S[(r1 + j) * DLD + r1 + k + 1] : 0.0; },
+                [&](int, int jj, int& klo, int& khi) { klo = jj; khi = h; },
+                [&](int i, int j, double v0, double v1) {
+                    tmp[i * TLD + j] = v0;
+                    tmp[i * TLD + j + 1] = v1;
+                },
+                warp, NW, lane);
+            __syncthreads();
+            // T21 = -T22 tmp : k in [0, i0 + 8)  (T22 lower triangular)
+            cta_gemm8(
+                hb, hb, false, [&](int i, int k) { return k <= i ? S[(r2 + k) * DLD + r2 + i + 1] : 0.0; },
+                [&](int k, int j) { return tmp[k * TLD + j]; },
+                [&](int ii, int, int& klo, int& khi) { klo = 0; khi = ii + 8; },
+                [&](int i, int j, double v0, double v1) {
+                    S[(r1 + j) * DLD + r2 + i + 1] = -v0;       // T(r2+i, r1+j)
+                    S[(r1 + j + 1) * DLD + r2 + i + 1] = -v1;
+                },
+                warp, NW, lane);
+            __syncthreads();
+        }
+    }
+
+    // write back: L11 with zeroed upper triangle, inv(L11) dense 128x128 (zero upper)
+    double* inv = invd + b * sInvd;
+    for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
+        int i = e / DB, j = e % DB;
+        if (i < nb && j < nb) Ab[(int64_t)i * ld + j] = (j <= i) ? S[i * DLD + j] : 0.0;
+        inv[e] = (j <= i) ? S[j * DLD + i + 1] : 0.0;
+    }
+    if (tid < DB) red[tid] = log(S[tid * DLD + tid]);
+    __syncthreads();
+    for (int off = DB / 2; off > 0; off >>= 1) {
+        if (tid < off) red[tid] += red[tid + off];
+        __syncthreads();
+    }
+    if (tid == 0) logdet_part[b * nblk + blk] = red[0];
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3: triangular solves.  One launch per 128-column block; every CTA first recomputes the block's
 // solution with the stored inverse of the diagonal block (128x128 GEMV, L2 resident) and then applies
 // it to its own slice of the remaining right-hand side, so a sweep streams L exactly once.
@@ -650,16 +858,30 @@ void launch_grad_trace(const double* X, int64_t sX, int n, int dp, Hyper h, cons
     CUGP_CUDA(cudaGetLastError());
 }
 
+static int g_diag_variant = 1;  // 1: blocked (DMMA) kernel, 0: column-at-a-time kernel
+void set_diag_variant(int v) { g_diag_variant = v; }
+
 void launch_potrf_diag(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd, double* logdet_part,
                        int nblk, int blk, int batch, cudaStream_t st) {
-    constexpr size_t smem = (size_t)DB * DLD * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        CUGP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    if (g_diag_variant == 0) {
+        constexpr size_t smem = (size_t)DB * DLD * sizeof(double);
+        static bool configured = false;
+        if (!configured) {
+            CUGP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        potrf_diag_kernel<<<batch, DIAG_THREADS, smem, st>>>(A, ld, sA, n, j0, invd + (int64_t)blk * DB * DB, sInvd,
+                                                             logdet_part, nblk, blk);
+    } else {
+        constexpr size_t smem = (size_t)(DB * DLD + 64 * TLD + DB + 2 * SB + DB) * sizeof(double);
+        static bool configured = false;
+        if (!configured) {
+            CUGP_CUDA(cudaFuncSetAttribute(potrf_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        potrf_diag_blocked_kernel<<<batch, DIAG_THREADS, smem, st>>>(A, ld, sA, n, j0, invd + (int64_t)blk * DB * DB,
+                                                                     sInvd, logdet_part, nblk, blk);
     }
-    potrf_diag_kernel<<<batch, DIAG_THREADS, smem, st>>>(A, ld, sA, n, j0, invd + (int64_t)blk * DB * DB, sInvd,
-                                                         logdet_part, nblk, blk);
     CUGP_CUDA(cudaGetLastError());
 }
 

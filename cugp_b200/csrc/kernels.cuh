@@ -42,6 +42,8 @@ size_t grad_trace_partials(int n, int batch);  // doubles needed in `partials`
 void launch_potrf_diag(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd,
                        double* logdet_part, int nblk, int blk, int batch, cudaStream_t st);
 
+void set_diag_variant(int v);  // 1 (default): blocked DMMA kernel; 0: column-at-a-time kernel
+
 // ---- K3: blocked triangular solves L z = y, L^T alpha = z (matrixops.cpp:145-164) with the stored
 // inverses of the diagonal blocks; one launch per 128-column block and sweep.
 void launch_trsv_forward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd,

@@ -10,11 +10,12 @@ namespace cugp {
 
 namespace {
 
-__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, long long* cycles = nullptr) {
     double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
     double c[16][2];
 #pragma unroll
     for (int j = 0; j < 16; j++) c[j][0] = c[j][1] = 0.0;
+    const long long t0 = clock64();
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int j = 0; j < 16; j++)
@@ -22,10 +23,12 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
                          : "+d"(c[j][0]), "+d"(c[j][1])
                          : "d"(a), "d"(b));
     }
+    const long long t1 = clock64();
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < 16; j++) s += c[j][0] + c[j][1];
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (cycles && blockIdx.x == 0 && threadIdx.x == 0) cycles[0] = t1 - t0;
 }
 
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
@@ -103,6 +106,32 @@ void probe_fp64_peak(float target_ms, double* dmma_tflops, double* dfma_tflops) 
     }
     CUGP_CUDA(cudaGetLastError());
     cudaFree(out);
+}
+
+// DMMA throughput over one launch of about `target_ms` milliseconds, one 256-thread CTA per SM (8 warps: the GEMM's
+// occupancy), and the SM clock that launch actually ran at (clock64 ticks of one CTA / event time): a short launch
+// gives the burst peak, a long one what the power limit sustains.
+void probe_dmma(float target_ms, double* tflops, double* sm_mhz) {
+    int dev = 0, sms = 148;
+    CUGP_CUDA(cudaGetDevice(&dev));
+    CUGP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = sms, threads = 256;
+    double* out = nullptr;
+    long long* cyc = nullptr;
+    CUGP_CUDA(cudaMalloc(&out, (size_t)grid * threads * sizeof(double)));
+    CUGP_CUDA(cudaMalloc(&cyc, sizeof(long long)));
+    dmma_peak_kernel<<<grid, threads>>>(out, 1000, cyc);
+    CUGP_CUDA(cudaDeviceSynchronize());
+    int iters = 20000;
+    float ms = time_ms([&] { dmma_peak_kernel<<<grid, threads>>>(out, iters, cyc); }, 0);
+    iters = (int)std::min(2.0e9, std::max(2000.0, iters * (double)target_ms / std::max(ms, 1e-3f)));
+    ms = time_ms([&] { dmma_peak_kernel<<<grid, threads>>>(out, iters, cyc); }, 0);
+    long long c = 0;
+    CUGP_CUDA(cudaMemcpy(&c, cyc, sizeof(c), cudaMemcpyDeviceToHost));
+    *tflops = (double)grid * threads * iters * (16.0 * 512.0 / 32.0) / (ms * 1e-3) / 1e12;
+    *sm_mhz = (double)c / (ms * 1e-3) / 1e6;
+    cudaFree(out);
+    cudaFree(cyc);
 }
 
 void probe_gemm(int M, int N, int K, int iters, double* tflops) {

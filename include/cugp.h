@@ -50,6 +50,10 @@ int cugp_set_device(int device);            /* one process per GPU: call before 
 long cugp_launch_count(void);
 void cugp_launch_count_reset(void);
 
+/* Tuning knobs (tests and benchmarks).  "potrf_nb": outer block width of the two-level blocked Cholesky, a multiple
+ * of 128; 0 = choose by matrix size. */
+int cugp_set_tuning(const char *key, long value);
+
 /* ---- Covsum (cpp_serial_gp/covkernel.h:3-38) ------------------------------------------------------ */
 /* Covsum::Covsum(int n, int d), covkernel.cpp:13-36.  d <= 64. */
 int cugp_covsum_create(int n, int d, cugp_covsum **out);
@@ -149,6 +153,9 @@ int cugp_bcm_predict(cugp_bcm *h, const double *Xtest, int m, double *mean, doub
 /* Sustained FP64 DMMA (mma.sync.m8n8k4.f64) and DFMA throughput of this GPU in TFLOP/s, register resident,
  * timed with CUDA events for about `ms` milliseconds each: the measured FP64 roofline denominators. */
 int cugp_probe_fp64_peak(float ms, double *dmma_tflops, double *dfma_tflops);
+/* One DMMA-only launch of about `ms` milliseconds (8 warps per SM, register resident): TFLOP/s and the SM clock it
+ * ran at.  ms ~ 10 gives the burst peak (a kernel timed alone), ms ~ 1000 the sustained one (inside a long step). */
+int cugp_probe_dmma(float ms, double *tflops, double *sm_mhz);
 /* C[M x N] (+)= alpha * A B^T on the DMMA GEMM with device-resident random operands; returns TFLOP/s. */
 int cugp_probe_gemm(int M, int N, int K, int iters, double *tflops);
 /* Kernel-level test hook: one launch of the DMMA GEMM template on host operands.

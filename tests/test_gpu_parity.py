@@ -69,6 +69,15 @@ def test_gemm_triangular_ranges(config):
     C0 = rng.standard_normal((n, n))
     out, _ = _gemm(P, P, C0, -1.0, 1.0, 1, 1, 1, config)
     assert np.allclose(np.tril(out), np.tril(C0 - P @ P.T), rtol=1e-13, atol=1e-12)
+    # lower trapezoid (panel update of the two-level Cholesky): M > N, tiles with ti >= tj only
+    Pn = P[:N + 7]
+    C1 = rng.standard_normal((n, N + 7))
+    out, _ = _gemm(P, Pn, C1, -1.0, 1.0, 1, 1, 1, config)
+    ref = C1 - P @ Pn.T
+    bs = 128 if config == 0 else 64
+    mask = (np.arange(n)[:, None] // bs) >= (np.arange(N + 7)[None, :] // bs)
+    assert np.allclose(out[mask], ref[mask], rtol=1e-13, atol=1e-12)
+    assert np.array_equal(out[~mask], C1[~mask])          # tiles above the diagonal are not touched
     # predictive variance epilogue: column sums of squares of T Kstar^T, per row tile
     Ks = rng.standard_normal((N, n))
     _, S = _gemm(T, Ks, np.zeros((n, N)), 1.0, 0.0, 1, 1, 1 << 3, config, css=True)
@@ -97,6 +106,24 @@ def test_matrixops_vs_oracle(n):
         Ki, Kio = cg.compute_K_inverse(K), PORT.k_inverse(K)
         assert np.linalg.norm(Ki - Kio) <= 1e-10 * np.linalg.norm(Kio)
         assert np.array_equal(Ki, Ki.T)
+
+
+@pytest.mark.parametrize("n,nb", [(700, 256), (1000, 512), (1300, 384), (520, 1024)])
+def test_two_level_cholesky(n, nb):
+    """The outer block width only changes the order of the trailing updates: L must still match the oracle."""
+    K, y = _spd(n, n + 1)
+    Lo = PORT.cholesky(K)
+    try:
+        assert lib().cugp_set_tuning(b"potrf_nb", nb) == 0
+        L = cg.get_cholesky(K)
+        q, ld = cg.compute_chol_and_det(K, y)
+    finally:
+        lib().cugp_set_tuning(b"potrf_nb", 0)
+    assert np.all(np.triu(L, 1) == 0.0)
+    assert np.linalg.norm(L - Lo) <= 1e-12 * np.linalg.norm(Lo)
+    qo, ldo = PORT.chol_and_det(K, y)
+    assert abs(q - qo) <= 1e-10 * abs(qo) and abs(ld - ldo) <= 1e-11 * max(1.0, abs(ldo))
+    assert lib().cugp_set_tuning(b"potrf_nb", 100) != 0 and lib().cugp_set_tuning(b"nope", 1) != 0
 
 
 def test_non_pd_is_nan_not_an_error():
