@@ -58,6 +58,8 @@ SIGNATURES = {
     "cugp_chol_and_det": (C.c_int, [dp, dp, C.c_int, dp, dp]),
     "cugp_kinv_y": (C.c_int, [dp, dp, dp, C.c_int]),
     "cugp_k_inverse": (C.c_int, [dp, dp, C.c_int]),
+    "cugp_tri_solve_matrix": (C.c_int, [dp, dp, dp, C.c_int, C.c_int]),
+    "cugp_bcm_dims": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cugp_bcm_create": (C.c_int, [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "cugp_bcm_destroy": (C.c_int, [C.c_void_p]),
     "cugp_bcm_set_loghyper": (C.c_int, [C.c_void_p, dp]),

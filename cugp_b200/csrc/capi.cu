@@ -138,6 +138,10 @@ int cugp_set_tuning(const char* key, long value) {
         set_potrf_outer_width((int)value);
         return CUGP_OK;
     }
+    if (std::strcmp(key, "gemm_kernel") == 0) {
+        set_gemm_variant(value != 0);
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "diag_kernel") == 0) {
         set_diag_variant(value != 0);
         return CUGP_OK;
@@ -455,6 +459,49 @@ int cugp_k_inverse(const double* K, double* Kinv, int n) {
     CUGP_CATCH
 }
 
+// matrix_forward_substitution (matrixops.cpp:330-340): L X = B, L lower triangular; matrix_backward_substitution
+// (matrixops.cpp:361-372): U X = B, U upper triangular.  X = inv(L) B resp. inv(U) B = inv(U^T)^T B on the DMMA GEMM.
+int cugp_tri_solve_matrix(const double* Tri, const double* Bm, double* X, int n, int upper) {
+    CUGP_TRY
+    if (!Tri || !Bm || !X || n <= 0) return CUGP_ERR_INVALID;
+    if (int rc = require_device()) return rc;
+    GpBatch g(1, n, 1);
+    track(&g);
+    struct Untrack { GpBatch* g; ~Untrack() { untrack(g); } } u{&g};
+    std::vector<double> Lh;
+    const double* src = Tri;
+    if (upper) {  // work with L = U^T
+        Lh.resize((size_t)n * n);
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j <= i; j++) Lh[(size_t)i * n + j] = Tri[(size_t)j * n + i];
+        src = Lh.data();
+    }
+    load_matrix(g, src);
+    g.ensure_TW();
+    const int64_t sI = (int64_t)g.nblk * kDiag * kDiag;
+    launch_trtri_diag(g.Kb, g.ld, g.mat_stride(), n, g.invd, sI, 1, g.st);
+    g.launches += g.nblk;
+    CUGP_CUDA(cudaMemsetAsync(g.Tb, 0, (size_t)n * g.ld * 8, g.st));
+    trtri_recursive(g.Kb, g.Tb, g.Wb, g.ld, g.mat_stride(), n, g.invd, sI, 1, g.st, &g.launches);
+    // B into Kb (L is no longer needed), X into Wb
+    CUGP_CUDA(cudaMemcpy2DAsync(g.Kb, (size_t)g.ld * 8, Bm, (size_t)n * 8, (size_t)n * 8, (size_t)n, cudaMemcpyHostToDevice, g.st));
+    GemmParams p{};
+    p.A = g.Tb; p.lda = g.ld;
+    p.B = g.Kb; p.ldb = g.ld;
+    p.C = g.Wb; p.ldc = g.ld;
+    p.M = n; p.N = n; p.K = n;
+    p.alpha = 1.0; p.beta = 0.0;
+    p.batch = 1;
+    if (upper) p.klo_ti = 1;  // X = T^T B : T stored [K][M], k >= i
+    else p.khi_ti = 1;        // X = T B   : T stored [M][K], k <= i
+    launch_gemm(p, !upper, false, pick_config(n, n, 1, false), g.st);
+    g.launches++;
+    CUGP_CUDA(cudaMemcpy2DAsync(X, (size_t)n * 8, g.Wb, (size_t)g.ld * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDeviceToHost, g.st));
+    g.sync();
+    return CUGP_OK;
+    CUGP_CATCH
+}
+
 }  // extern "C"
 
 // ---- BCM --------------------------------------------------------------------------------------------
@@ -530,6 +577,13 @@ int cugp_bcm_create(const double* X, const double* y, int N, int D, int K, int r
     *out = h.release();
     return CUGP_OK;
     CUGP_CATCH
+}
+int cugp_bcm_dims(cugp_bcm* h, int* N, int* D, int* K) {
+    if (!h) return CUGP_ERR_INVALID;
+    if (N) *N = h->N;
+    if (D) *D = h->D;
+    if (K) *K = h->K;
+    return CUGP_OK;
 }
 int cugp_bcm_destroy(cugp_bcm* h) {
     delete h;

@@ -237,6 +237,334 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) dgemm_dmma_kernel(co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-specialised variant (the default): a producer warp streams the operand tiles with zero-filling
+// 16-byte cp.async (LDGSTS) whose completion is tracked by per-stage mbarriers
+// (cp.async.mbarrier.arrive.noinc); the consumer warps only wait on a barrier, load fragments and issue
+// DMMA -- no CTA-wide __syncthreads and no address arithmetic in the math warps.  (Measured: feeding the
+// stages with one 1-D cp.async.bulk per 256-byte row instead capped the kernel at 19 TFLOP/s -- the copy
+// engine sustains only about one such request per 60 clocks per SM.)  BK = 32 halves the per-stage fixed costs of the cp.async kernel above.
+// Tiles are rasterised in strips of 8 tile columns so the 148 resident CTAs share a few operand
+// panels (L2 hits instead of HBM re-reads when the panels exceed the 126 MB L2).
+// ------------------------------------------------------------------------------------------------
+constexpr int WBK = 32;        // k-depth of one stage
+constexpr int WPAD = 4;        // (WBK + WPAD) % 16 == 4 and (ROWS + WPAD) % 16 == 4: conflict-free 8-byte fragments
+constexpr int RASTER_W = 8;    // tile columns per raster strip
+
+template <int ROWS, bool KC>
+__host__ __device__ constexpr int ws_tile_doubles() {
+    return KC ? ROWS * (WBK + WPAD) : WBK * (ROWS + WPAD);
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Linear block index -> output tile.  lower: tiles with ti >= tj of a tm x tn (tm >= tn) trapezoid.
+__device__ __forceinline__ void raster_tile(int x, int tm, int tn, bool lower, int& ti, int& tj) {
+    int s = 0, w, rows;
+    if (lower) {
+        for (;;) {
+            w = min(RASTER_W, tn - s * RASTER_W);
+            rows = tm - s * RASTER_W;
+            const int cnt = w * (w + 1) / 2 + (rows - w) * w;
+            if (x < cnt) break;
+            x -= cnt;
+            s++;
+        }
+        const int tri = w * (w + 1) / 2;
+        if (x < tri) {
+            int r = (int)((sqrtf(8.f * (float)x + 1.f) - 1.f) * 0.5f);
+            while ((r + 1) * (r + 2) / 2 <= x) r++;
+            while (r * (r + 1) / 2 > x) r--;
+            ti = s * RASTER_W + r;
+            tj = s * RASTER_W + (x - r * (r + 1) / 2);
+        } else {
+            x -= tri;
+            ti = s * RASTER_W + w + x / w;
+            tj = s * RASTER_W + x % w;
+        }
+    } else {
+        const int per = RASTER_W * tm;
+        s = x / per;
+        x -= s * per;
+        w = min(RASTER_W, tn - s * RASTER_W);
+        ti = x / w;
+        tj = s * RASTER_W + x % w;
+    }
+}
+
+constexpr int NPW = 1;         // producer warps
+
+__device__ __forceinline__ void cp_async_arrive_noinc(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Producer side of one stage for one operand: zero-filling 16-byte cp.async (LDGSTS) issued by the NPW*32 producer
+// lanes; each lane keeps the same k-chunk (KC) / row pair (RC) for the whole tile so the loop is one LDGSTS and one
+// pointer bump per 16 bytes.
+template <int ROWS, bool KC>
+__device__ __forceinline__ void produce_operand(double* smem, const double* __restrict__ g, int64_t ld, int row0,
+                                                int rows_total, int k0, int k_hi, int pl) {
+    constexpr int NL = NPW * 32;
+    if (KC) {
+        constexpr int CH = WBK / 2;          // 16-byte chunks per row
+        constexpr int RSTEP = NL / CH;       // rows advanced per iteration
+        const int kc = (pl % CH) * 2, r0 = pl / CH;
+        const int bytes = min(max((k_hi - (k0 + kc)) * 8, 0), 16);
+        const int rows = min(ROWS, rows_total - row0);
+        const double* src = g + (int64_t)(row0 + r0) * ld + k0 + kc;
+        double* dst = smem + r0 * (WBK + WPAD) + kc;
+#pragma unroll 4
+        for (int r = r0; r < ROWS; r += RSTEP) {
+            const int nb = r < rows ? bytes : 0;
+            cp_async16(dst, nb ? src : g, nb);
+            src += (int64_t)RSTEP * ld;
+            dst += RSTEP * (WBK + WPAD);
+        }
+    } else {
+        constexpr int CH = ROWS / 2;         // 16-byte chunks per k-row
+        constexpr int PER = CH / NL;         // chunks of one k-row per lane (CH >= NL for ROWS >= 64, NPW = 1)
+        static_assert(CH % NL == 0, "producer lanes must tile a k-row");
+#pragma unroll 2
+        for (int kr = 0; kr < WBK; kr++) {
+            const int gk = k0 + kr;
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int mc = (pl + u * NL) * 2;
+                int nb = 0;
+                if (gk < k_hi) nb = min(max((rows_total - (row0 + mc)) * 8, 0), 16);
+                cp_async16(smem + kr * (ROWS + WPAD) + mc, nb ? g + (int64_t)gk * ld + row0 + mc : g, nb);
+            }
+        }
+    }
+}
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_kernel(const GemmParams p) {
+    constexpr int NCW = WARPS_M * WARPS_N;  // consumer warps
+    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+    constexpr int MI = WM / 8, NI = WN / 8;
+    constexpr int A_SZ = ws_tile_doubles<BM, A_KC>();
+    constexpr int B_SZ = ws_tile_doubles<BN, B_KC>();
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + NSTAGE * A_SZ;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + NSTAGE * (A_SZ + B_SZ));
+    unsigned long long* empty = full + NSTAGE;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    int ti, tj;
+    raster_tile(blockIdx.x, tiles_m, tiles_n, p.lower_tiles != 0, ti, tj);
+    const int m0 = ti * BM, n0 = tj * BN;
+    const int64_t b = blockIdx.y;
+    int64_t offA, offB, offC;
+    if (p.batch_inner > 1) {
+        const int64_t bi = b % p.batch_inner, bo = b / p.batch_inner;
+        offA = bi * p.sA + bo * p.sA2;
+        offB = bi * p.sB + bo * p.sB2;
+        offC = bi * p.sC + bo * p.sC2;
+    } else {
+        offA = b * p.sA;
+        offB = b * p.sB;
+        offC = b * p.sC;
+    }
+    const double* __restrict__ A = p.A + offA;
+    const double* __restrict__ B = p.B + offB;
+
+    int k_lo = 0, k_hi = p.K;
+    if (p.klo_ti) k_lo = max(k_lo, m0);
+    if (p.klo_tj) k_lo = max(k_lo, n0);
+    if (p.khi_ti) k_hi = min(k_hi, m0 + BM);
+    if (p.khi_tj) k_hi = min(k_hi, n0 + BN);
+    const int nk = k_hi > k_lo ? (k_hi - k_lo + WBK - 1) / WBK : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; s++) {
+            mbar_init(&full[s], NPW * 32);
+            mbar_init(&empty[s], NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= NCW) {
+        // ------------------------------ producer warp(s) ------------------------------
+        if (p.beta != 0.0 && !p.colsumsq) {  // pull the C tile into L2 while the main loop runs
+            const double* C = p.C + offC;
+            const int rows = min(BM, p.M - m0), cols = min(BN, p.N - n0);
+            for (int r = lane; r < rows; r += 32) {
+                const double* row = C + (int64_t)(m0 + r) * p.ldc + n0;
+                for (int c = 0; c < cols; c += 16) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + c));
+            }
+        }
+        const int pl = tid - NCW * 32;  // producer lane
+        for (int kt = 0; kt < nk; kt++) {
+            const int s = kt % NSTAGE;
+            if (kt >= NSTAGE) mbar_wait(&empty[s], (unsigned)((kt / NSTAGE - 1) & 1));
+            const int k0 = k_lo + kt * WBK;
+            produce_operand<BM, A_KC>(As + s * A_SZ, A, p.lda, m0, p.M, k0, k_hi, pl);
+            produce_operand<BN, B_KC>(Bs + s * B_SZ, B, p.ldb, n0, p.N, k0, k_hi, pl);
+            cp_async_arrive_noinc(&full[s]);  // this lane's arrival fires when its copies above have landed
+        }
+        cp_async_wait<0>();
+        return;
+    }
+
+    // ------------------------------ consumer warps ------------------------------
+    const int g = lane >> 2, q = lane & 3;
+    const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; i++)
+#pragma unroll
+        for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < nk; kt++) {
+        const int s = kt % NSTAGE;
+        mbar_wait(&full[s], (unsigned)((kt / NSTAGE) & 1));
+        const double* as = As + s * A_SZ;
+        const double* bs = Bs + s * B_SZ;
+#pragma unroll
+        for (int kk = 0; kk < WBK; kk += 4) {
+            double af[MI], bf[NI];
+#pragma unroll
+            for (int i = 0; i < MI; i++)
+                af[i] = A_KC ? as[(wm0 + i * 8 + g) * (WBK + WPAD) + kk + q] : as[(kk + q) * (BM + WPAD) + wm0 + i * 8 + g];
+#pragma unroll
+            for (int j = 0; j < NI; j++)
+                bf[j] = B_KC ? bs[(wn0 + j * 8 + g) * (WBK + WPAD) + kk + q] : bs[(kk + q) * (BN + WPAD) + wn0 + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < MI; i++)
+#pragma unroll
+                for (int j = 0; j < NI; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    if (p.colsumsq) {
+        // Epilogue for the predictive variance: sum over this tile's rows of (alpha*acc)^2, per column.
+        asm volatile("bar.sync 1, %0;\n" ::"n"(NCW * 32) : "memory");  // all consumers are done with the stages
+        double* red = smem;  // [WARPS_M][BN]
+#pragma unroll
+        for (int j = 0; j < NI; j++) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < MI; i++) {
+                int row = m0 + wm0 + i * 8 + g;
+                if (row < p.M) {
+                    double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+                    s0 += v0 * v0;
+                    s1 += v1 * v1;
+                }
+            }
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            }
+            if (g == 0) {
+                red[(warp / WARPS_N) * BN + wn0 + j * 8 + 2 * q] = s0;
+                red[(warp / WARPS_N) * BN + wn0 + j * 8 + 2 * q + 1] = s1;
+            }
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(NCW * 32) : "memory");
+        double* out = p.colsumsq + b * p.sCss + (int64_t)ti * p.N;
+        for (int c = tid; c < BN; c += NCW * 32) {
+            if (n0 + c < p.N) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < WARPS_M; w++) s += red[w * BN + c];
+                out[n0 + c] = s;
+            }
+        }
+        return;
+    }
+
+    double* __restrict__ C = p.C + offC;
+    const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < MI; i++) {
+        int row = m0 + wm0 + i * 8 + g;
+        if (row >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < NI; j++) {
+            int col = n0 + wn0 + j * 8 + 2 * q;
+            if (col >= p.N) continue;
+            double* cp = C + (int64_t)row * p.ldc + col;
+            double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+            if (col + 1 < p.N && vec_ok) {
+                if (p.beta != 0.0) {
+                    double2 old = *reinterpret_cast<const double2*>(cp);
+                    v0 += p.beta * old.x;
+                    v1 += p.beta * old.y;
+                }
+                *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+            } else {
+                if (p.beta != 0.0) v0 += p.beta * cp[0];
+                cp[0] = v0;
+                if (col + 1 < p.N) {
+                    if (p.beta != 0.0) v1 += p.beta * cp[1];
+                    cp[1] = v1;
+                }
+            }
+        }
+    }
+}
+
+static int g_gemm_variant = 1;  // 1: warp-specialised bulk-copy kernel, 0: cp.async kernel
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC>
+void launch_ws(const GemmParams& p, cudaStream_t stream) {
+    constexpr int NT = (WARPS_M * WARPS_N + NPW) * 32;
+    constexpr size_t smem =
+        (size_t)NSTAGE * (ws_tile_doubles<BM, A_KC>() + ws_tile_doubles<BN, B_KC>()) * sizeof(double) + 2 * NSTAGE * 8;
+    static_assert(smem <= 227 * 1024, "stage buffers exceed shared memory");
+    static bool configured = false;
+    auto kern = dgemm_ws_kernel<BM, BN, WARPS_M, WARPS_N, NSTAGE, A_KC, B_KC>;
+    if (!configured) {
+        CUGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int tiles_m = cdiv(p.M, BM), tiles_n = cdiv(p.N, BN);
+    int64_t tiles = (int64_t)tiles_m * tiles_n;
+    if (p.lower_tiles) {
+        if (BM != BN || tiles_m < tiles_n) throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};
+        tiles = (int64_t)tiles_n * (tiles_n + 1) / 2 + (int64_t)(tiles_m - tiles_n) * tiles_n;
+    }
+    if (tiles <= 0 || p.batch <= 0) return;
+    dim3 grid((unsigned)tiles, (unsigned)p.batch);
+    kern<<<grid, NT, smem, stream>>>(p);
+    CUGP_CUDA(cudaGetLastError());
+}
+
 template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KC, bool B_KC>
 void launch_one(const GemmParams& p, cudaStream_t stream) {
     constexpr int NT = WARPS_M * WARPS_N * 32;
@@ -259,8 +587,15 @@ void launch_one(const GemmParams& p, cudaStream_t stream) {
     CUGP_CUDA(cudaGetLastError());
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE>
 void launch_layout(const GemmParams& p, bool a_kc, bool b_kc, cudaStream_t stream) {
+    if (g_gemm_variant == 1) {
+        if (a_kc && b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, true, true>(p, stream);
+        else if (a_kc && !b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, true, false>(p, stream);
+        else if (!a_kc && !b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, false, false>(p, stream);
+        else launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, false, true>(p, stream);
+        return;
+    }
     if (a_kc && b_kc) launch_one<BM, BN, WARPS_M, WARPS_N, true, true>(p, stream);
     else if (a_kc && !b_kc) launch_one<BM, BN, WARPS_M, WARPS_N, true, false>(p, stream);
     else if (!a_kc && !b_kc) launch_one<BM, BN, WARPS_M, WARPS_N, false, false>(p, stream);
@@ -268,6 +603,8 @@ void launch_layout(const GemmParams& p, bool a_kc, bool b_kc, cudaStream_t strea
 }
 
 }  // namespace
+
+void set_gemm_variant(int v) { g_gemm_variant = v; }
 
 int gemm_tile_m(GemmConfig cfg) { return cfg == GEMM_BIG ? 128 : 64; }
 
@@ -279,9 +616,9 @@ GemmConfig pick_config(int M, int N, int batch, bool lower_tiles) {
 
 void launch_gemm(const GemmParams& p, bool a_kc, bool b_kc, GemmConfig cfg, cudaStream_t stream) {
     switch (cfg) {
-        case GEMM_BIG: launch_layout<128, 128, 2, 4>(p, a_kc, b_kc, stream); break;
-        case GEMM_TALL: launch_layout<64, 128, 2, 4>(p, a_kc, b_kc, stream); break;
-        default: launch_layout<64, 64, 2, 2>(p, a_kc, b_kc, stream); break;
+        case GEMM_BIG: launch_layout<128, 128, 2, 4, 3>(p, a_kc, b_kc, stream); break;
+        case GEMM_TALL: launch_layout<64, 128, 2, 4, 3>(p, a_kc, b_kc, stream); break;
+        default: launch_layout<64, 64, 2, 2, 4>(p, a_kc, b_kc, stream); break;
     }
 }
 

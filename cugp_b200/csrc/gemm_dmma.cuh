@@ -40,5 +40,6 @@ void launch_gemm(const GemmParams& p, bool a_kc, bool b_kc, GemmConfig cfg, cuda
 // Picks BIG when the grid fills the chip, SMALL otherwise.
 GemmConfig pick_config(int M, int N, int batch, bool lower_tiles);
 int gemm_tile_m(GemmConfig cfg);
+void set_gemm_variant(int v);  // 1 (default): warp-specialised bulk-copy kernel; 0: cp.async kernel
 
 }  // namespace cugp

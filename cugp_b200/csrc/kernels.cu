@@ -375,9 +375,10 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
     double* inv = invd + b * sInvd;
     for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
         int i = e / DB, j = e % DB;
-        if (i < nb && j < nb) Ab[(int64_t)i * ld + j] = (j <= i) ? S[i * DLD + j] : 0.0;
+        if (factor && i < nb && j < nb) Ab[(int64_t)i * ld + j] = (j <= i) ? S[i * DLD + j] : 0.0;
         inv[e] = (j <= i) ? S[j * DLD + i + 1] : 0.0;
     }
+    if (!logdet_part) return;
     if (tid < DB) red[tid] = log(S[tid * DLD + tid]);
     __syncthreads();
     for (int off = DB / 2; off > 0; off >>= 1) {
@@ -437,7 +438,7 @@ __device__ __forceinline__ void cta_gemm8(int mb, int nbk, bool lower, FA A, FB 
 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
     potrf_diag_blocked_kernel(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd,
-                              double* logdet_part, int nblk, int blk) {
+                              double* logdet_part, int nblk, int blk, int factor) {
     extern __shared__ __align__(16) double S[];
     double* tmp = S + DB * DLD;                // [64][TLD]
     double* rdiag = tmp + 64 * TLD;            // [128] reciprocals of L's diagonal
@@ -460,8 +461,12 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
     }
     __syncthreads();
 
+    if (!factor) {  // the block already holds a triangular factor: only its inverse is wanted
+        if (tid < DB) rdiag[tid] = 1.0 / S[tid * DLD + tid];
+        __syncthreads();
+    }
     // ---------------- Cholesky, panel by panel ----------------
-    for (int c0 = 0; c0 < DB; c0 += SB) {
+    for (int c0 = 0; factor && c0 < DB; c0 += SB) {
         if (warp == 0) {
             // 32x32 diagonal sub-block: lane i owns row i in registers (matrixops.cpp:74-98 on the sub-block).
             double a[SB];
@@ -583,9 +588,10 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
     double* inv = invd + b * sInvd;
     for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
         int i = e / DB, j = e % DB;
-        if (i < nb && j < nb) Ab[(int64_t)i * ld + j] = (j <= i) ? S[i * DLD + j] : 0.0;
+        if (factor && i < nb && j < nb) Ab[(int64_t)i * ld + j] = (j <= i) ? S[i * DLD + j] : 0.0;
         inv[e] = (j <= i) ? S[j * DLD + i + 1] : 0.0;
     }
+    if (!logdet_part) return;
     if (tid < DB) red[tid] = log(S[tid * DLD + tid]);
     __syncthreads();
     for (int off = DB / 2; off > 0; off >>= 1) {
@@ -880,8 +886,22 @@ void launch_potrf_diag(double* A, int64_t ld, int64_t sA, int n, int j0, double*
             configured = true;
         }
         potrf_diag_blocked_kernel<<<batch, DIAG_THREADS, smem, st>>>(A, ld, sA, n, j0, invd + (int64_t)blk * DB * DB,
-                                                                     sInvd, logdet_part, nblk, blk);
+                                                                     sInvd, logdet_part, nblk, blk, 1);
     }
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* invd, int64_t sInvd, int batch,
+                       cudaStream_t st) {
+    constexpr size_t smem = (size_t)(DB * DLD + 64 * TLD + DB + 2 * SB + DB) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        CUGP_CUDA(cudaFuncSetAttribute(potrf_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    for (int blk = 0; blk * DB < n; blk++)
+        potrf_diag_blocked_kernel<<<batch, DIAG_THREADS, smem, st>>>(const_cast<double*>(L), ld, sL, n, blk * DB,
+                                                                     invd + (int64_t)blk * DB * DB, sInvd, nullptr, 0, blk, 0);
     CUGP_CUDA(cudaGetLastError());
 }
 

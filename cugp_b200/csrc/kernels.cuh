@@ -42,6 +42,9 @@ size_t grad_trace_partials(int n, int batch);  // doubles needed in `partials`
 void launch_potrf_diag(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd,
                        double* logdet_part, int nblk, int blk, int batch, cudaStream_t st);
 
+// inverses of the 128x128 diagonal blocks of a given lower-triangular L (no factorisation): feeds trtri_recursive
+void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* invd, int64_t sInvd, int batch,
+                       cudaStream_t st);
 void set_diag_variant(int v);  // 1 (default): blocked DMMA kernel; 0: column-at-a-time kernel
 
 // ---- K3: blocked triangular solves L z = y, L^T alpha = z (matrixops.cpp:145-164) with the stored

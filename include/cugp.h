@@ -121,12 +121,17 @@ int cugp_kinv_y(const double *K, const double *y, double *alpha, int n);
 /* compute_K_inverse, matrixops.cpp:383-435: dense symmetric n x n */
 int cugp_k_inverse(const double *K, double *Kinv, int n);
 
+/* matrix_forward_substitution, matrixops.cpp:330-340 (upper = 0: Tri lower triangular, Tri X = B) and
+ * matrix_backward_substitution, matrixops.cpp:361-372 (upper = 1: Tri upper triangular); B and X are n x n. */
+int cugp_tri_solve_matrix(const double *Tri, const double *B, double *X, int n, int upper);
+
 /* ---- BCM (distributed_gp/BCM.h:2-27) ---------------------------------------------------------------- */
 /* BCM::BCM(X, y, N, D, K), BCM.cpp:85-110: K contiguous chunks of floor(N/K) rows, the last takes the
  * remainder.  One process per GPU: this process owns experts e with e % world == rank and keeps them device
  * resident; rank/world = 0/1 for a single GPU.  Data is copied (the reference keeps the caller's pointers). */
 int cugp_bcm_create(const double *X, const double *y, int N, int D, int K, int rank, int world, cugp_bcm **out);
 int cugp_bcm_destroy(cugp_bcm *h);
+int cugp_bcm_dims(cugp_bcm *h, int *N, int *D, int *K); /* any pointer may be NULL */
 /* BCM::set_BCM_log_hyperparam / set_BCM_loghyper_eigen, BCM.cpp:123-130, 205-212 */
 int cugp_bcm_set_loghyper(cugp_bcm *h, const double theta[3]);
 /* BCM::get_loghyperparam, BCM.cpp:200-204 */
