@@ -375,10 +375,9 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
     double* inv = invd + b * sInvd;
     for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
         int i = e / DB, j = e % DB;
-        if (factor && i < nb && j < nb) Ab[(int64_t)i * ld + j] = (j <= i) ? S[i * DLD + j] : 0.0;
+        if (i < nb && j < nb) Ab[(int64_t)i * ld + j] = (j <= i) ? S[i * DLD + j] : 0.0;
         inv[e] = (j <= i) ? S[j * DLD + i + 1] : 0.0;
     }
-    if (!logdet_part) return;
     if (tid < DB) red[tid] = log(S[tid * DLD + tid]);
     __syncthreads();
     for (int off = DB / 2; off > 0; off >>= 1) {
