@@ -207,10 +207,19 @@ def run_reference_arm(a):
 
 # --------------------------------------------------------------------------------------------------------------
 def fp64_probes(lib):
+    """Measured FP64 denominators: DMMA burst (10 ms launch) and sustained (2 s launch) with the SM clock each ran
+    at, DFMA for context, and a device copy."""
+    out = {}
+    for name, ms in (("dmma_burst", 10.0), ("dmma_sustained", 2000.0)):
+        tf, mhz = C.c_double(), C.c_double()
+        lib.cugp_probe_dmma(ms, C.byref(tf), C.byref(mhz))
+        out[name] = tf.value
+        out[name + "_sm_mhz"] = mhz.value
     dm, df, cp = C.c_double(), C.c_double(), C.c_double()
-    lib.cugp_probe_fp64_peak(400.0, C.byref(dm), C.byref(df))
+    lib.cugp_probe_fp64_peak(50.0, C.byref(dm), C.byref(df))
     lib.cugp_probe_copy(1 << 30, 10, C.byref(cp))
-    return dm.value, df.value, cp.value
+    out["dfma_probe"] = df.value
+    return out, cp.value
 
 
 def extra_c2(cg, torch, flush, n=4096, evals=6):
@@ -232,23 +241,47 @@ def extra_c2(cg, torch, flush, n=4096, evals=6):
     return 1.0 / statistics.median(ts[2:])
 
 
-def extra_c4(cg, torch, flush, m=10000):
-    """BCM 16 x 1500 prediction pts/s on this GPU alone (factorised experts resident; theta_C)."""
+def extra_c4(cg, torch, dist, flush, m=10000, reps=4):
+    """BCM 16 x 1500 on ALL ranks of this run (experts e % world == rank, NCCL allreduce of the moments):
+    prediction pts/s with factorised experts resident, and (LL, gradient) evaluations/s; theta_C."""
     d = np.load(os.path.join(ROOT, "tests", "golden", "data_si24000.npz"))
     from cugp_b200.loaders import synthetic_sine
     Xt, _ = synthetic_sine(m, 10, seed=7)
-    b = cg.BCM(d["X"], d["y"], K=16, rank=0, world=1)
+    b = cg.BCM(d["X"], d["y"], K=16)
     b.set_BCM_log_hyperparam(TH_C)
     b.loglik_and_gradient()
-    ts = []
-    for _ in range(4):
-        torch.cuda.synchronize()
-        t = time.perf_counter()
-        b.compute_BCM_test_means_and_var(Xt)
-        ts.append(time.perf_counter() - t)
-        flush()
+    b.compute_BCM_test_means_and_var(Xt)
+
+    def timed(fn):
+        ts = []
+        for _ in range(reps):
+            flush()
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t)
+        v = statistics.median(ts[1:])
+        if dist is not None:
+            tt = torch.tensor([v], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            v = float(tt.item())
+        return v
+
+    k = [0]
+
+    def ev():
+        k[0] += 1
+        b.set_BCM_log_hyperparam([TH_C[0] + 1e-7 * k[0], TH_C[1], TH_C[2]])
+        b.loglik_and_gradient()
+
+    t_pred = timed(lambda: b.compute_BCM_test_means_and_var(Xt))
+    t_eval = timed(ev)
     b.close()
-    return m / statistics.median(ts[1:])
+    return {"c4_bcm_pred_pts_per_s": m / t_pred, "c4_bcm_loglik_grad_evals_per_s": 1.0 / t_eval, "c4_gpus": b.world,
+            "c4_test_points": m}
 
 
 def main():
@@ -345,7 +378,12 @@ def main():
         # factorisation alone (events inside the library), for the record
         g.set_loghyperparam(theta_i())
         ms_cov, ms_chol = g.factorize_resident()
-        out["phases_ms"] = {"covariance": ms_cov, "cholesky": ms_chol, "cholesky_tflops": (n ** 3 / 3) / (ms_chol * 1e-3) / 1e12}
+        ms_solve = g.solve_resident()
+        tri_bytes = 4.0 * n * (n + 1)                  # lower triangle incl. diagonal, 8 B each
+        out["phases_ms"] = {"covariance": ms_cov, "cholesky": ms_chol, "solves": ms_solve,
+                            "cholesky_tflops": (n ** 3 / 3) / (ms_chol * 1e-3) / 1e12,
+                            "covariance_gbs": tri_bytes / (ms_cov * 1e-3) / 1e9,       # K1 writes the lower triangle once
+                            "solves_gbs": 2.0 * tri_bytes / (ms_solve * 1e-3) / 1e9}   # K3 streams L once per sweep
         config = {"workload": {"c5": f"C5 synthetic exact GP n={n} d=10: covariance build + blocked Cholesky + solves + LL",
                                "c3": f"C3 exact GP n={n} d=10 train + predict {a.m} points",
                                "c2": f"C2 exact GP n={n} d=10 hyper-parameter loop: LL + gradient per evaluation"}[a.workload],
@@ -379,12 +417,19 @@ def main():
                   "l2": "256 MB flush between steps"}
         b.close()
 
+    extra = None
+    if not a.no_extra and a.workload == "c5":   # collective: every rank takes part in the sharded BCM
+        try:
+            extra = extra_c4(cg, torch, dist, flush)
+        except Exception as e:  # the headline must still print
+            extra = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    dmma, dfma, copy_gbs = fp64_probes(L)
+    fp64, copy_gbs = fp64_probes(L)
+    dmma = fp64["dmma_sustained"]
     # cuBLAS DGEMM as a library ceiling for context only (never on the product path)
     try:
         A = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
@@ -400,21 +445,29 @@ def main():
         cublas = None
     if syrk_cnt:
         achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
-        out["roofline"] = {"bound": "tensor", "kernel": "dgemm_dmma_kernel (SYRK trailing update A22 -= L21 L21^T, lower tiles)",
-                           "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma, "traffic": None,
-                           "peak_source": "measured here: register-resident mma.sync.m8n8k4.f64 loop (cugp_probe_fp64_peak); "
-                                          "MEASURED_PEAKS.json has no FP64 entry",
-                           "frac_of_dfma_measured": achieved / dfma, "frac_of_nominal_37": achieved / NOMINAL_FP64_TFLOPS,
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp))
+        out["roofline"] = {"bound": "tensor", "kernel": "dgemm_ws_kernel<128,128> (Cholesky trailing update A22 -= P P^T, lower "
+                                                        "tiles, K = outer block width)",
+                           "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma, "traffic": traffic,
+                           "peak_source": "measured here, sustained: one 2 s launch of register-resident mma.sync.m8n8k4.f64 "
+                                          "(cugp_probe_dmma); MEASURED_PEAKS.json has no FP64 entry",
+                           "frac_of_nominal_37": achieved / NOMINAL_FP64_TFLOPS,
                            "launches_timed": syrk_cnt, "share_of_step": syrk_ms / ((a.steps + a.warmup) * ms),
-                           "algorithmic_flops_per_launch": "m(m+1)*128 for an m x m trailing block"}
-    out["fp64_peaks_tflops"] = {"dmma_probe": dmma, "dfma_probe": dfma, "cublas_dgemm_8192": cublas, "nominal": NOMINAL_FP64_TFLOPS}
+                           "algorithmic_flops_per_launch": "m(m+1)*K for an m x m trailing block (lower triangle, 2 flop/MAC)"}
+    out["fp64_peaks_tflops"] = dict(fp64, cublas_dgemm_8192=cublas, nominal=NOMINAL_FP64_TFLOPS)
     out["hbm"] = {"copy_probe_gbs": copy_gbs, "peak_gbs": pk.get("hbm_gbs"), "peak_source": pk_src}
+    if "phases_ms" in out and pk.get("hbm_gbs"):
+        out["phases_ms"]["covariance_frac_of_hbm"] = out["phases_ms"]["covariance_gbs"] / pk["hbm_gbs"]
+        out["phases_ms"]["solves_frac_of_hbm"] = out["phases_ms"]["solves_gbs"] / pk["hbm_gbs"]
     if not a.no_extra and a.workload == "c5":
         try:
-            out["extra"] = {"c2_loglik_grad_evals_per_s": extra_c2(cg, torch, flush),
-                            "c4_bcm_pred_pts_per_s_1gpu": extra_c4(cg, torch, flush)}
-        except Exception as e:  # the headline must still print
-            out["extra"] = {"error": repr(e)}
+            extra = dict(extra or {}, c2_loglik_grad_evals_per_s=extra_c2(cg, torch, flush))
+        except Exception as e:
+            extra = dict(extra or {}, c2_error=repr(e))
+        out["extra"] = extra
     n_s = 2048 if a.workload in ("c5", "c3") else 1024
     cpu = cpu_baseline("reference", n_s, TH_B)
     if a.workload == "c2":

@@ -147,6 +147,12 @@ class Covsum:
         return a.value, b.value
 
 
+    def solve_resident(self):
+        """Device ms of the two triangular sweeps + log-det + LL on the cached factor."""
+        a = C.c_float()
+        check(lib().cugp_covsum_solve_resident(self._h, C.byref(a)))
+        return a.value
+
     def profile(self, enable: bool = True):
         check(lib().cugp_covsum_profile(self._h, int(enable)))
 

@@ -323,6 +323,27 @@ int cugp_covsum_factorize_resident(cugp_covsum* h, float* ms_cov, float* ms_chol
     CUGP_CATCH
 }
 
+int cugp_covsum_solve_resident(cugp_covsum* h, float* ms_solve) {
+    CUGP_TRY
+    if (int rc = need_data(h)) return rc;
+    GpBatch& g = *h->gp;
+    g.factorize();
+    g.have_alpha = false;
+    cudaEvent_t e0, e1;
+    CUGP_CUDA(cudaEventCreate(&e0));
+    CUGP_CUDA(cudaEventCreate(&e1));
+    CUGP_CUDA(cudaEventRecord(e0, g.st));
+    g.solve();
+    CUGP_CUDA(cudaEventRecord(e1, g.st));
+    CUGP_CUDA(cudaEventSynchronize(e1));
+    float a = 0;
+    CUGP_CUDA(cudaEventElapsedTime(&a, e0, e1));
+    if (ms_solve) *ms_solve = a;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return CUGP_OK;
+    CUGP_CATCH
+}
+
 int cugp_covsum_profile(cugp_covsum* h, int enable) {
     CUGP_TRY
     if (!h) return CUGP_ERR_INVALID;

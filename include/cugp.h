@@ -105,9 +105,14 @@ int cugp_covsum_alpha_resident(cugp_covsum *h, double *alpha);
  * (CUDA events on the launching stream), for the FP64 roofline (n^3/3 flop). */
 int cugp_covsum_factorize_resident(cugp_covsum *h, float *ms_cov, float *ms_chol);
 
+/* Forward + backward solves, log-det and LL alone on the cached factor (factorises first if needed): device time
+ * in ms, for the HBM roofline of the solves (2 * 4 n (n+1) bytes: L is streamed once per sweep). */
+int cugp_covsum_solve_resident(cugp_covsum *h, float *ms_solve);
+
 /* Dominant-kernel timing for the roofline: with profiling enabled every SYRK trailing-update launch of the
  * Cholesky is bracketed by CUDA events on its stream.  profile_read returns, since the last profile(h, 1):
- * the summed launch duration (ms), their algorithmic flops (sum of m(m+1)*128 per launch) and the count. */
+ * the summed launch duration (ms), their algorithmic flops (sum of m(m+1)*K per launch, K = outer block width)
+ * and the count. */
 int cugp_covsum_profile(cugp_covsum *h, int enable);
 int cugp_covsum_profile_read(cugp_covsum *h, double *syrk_ms, double *syrk_flops, long *launches);
 

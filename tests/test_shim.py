@@ -1,0 +1,161 @@
+"""The drop-in boundary: the header shim (include/cugp_shim) re-declares the reference's C++ classes and free
+functions with their exact signatures on top of the C ABI.
+
+* CPU (here): tests/shim/shim_probe.cpp, which calls every member, compiles and links against libcugp.so; and, where
+  /root/reference exists, the reference's OWN drivers (cpp_serial_gp/serial_gp.cpp, distributed_gp/
+  distributed_ver1.cpp) compile UNCHANGED with the shim headers in place of covkernel.h / matrixops.h / BCM.h.
+  The binaries land in oracle/_ref/drivers/ (git-ignored, travels to the GPU box).
+* GPU: the binaries run; shim_probe's numbers equal the Python mirror's, and the reference driver's own optimiser
+  loop (distributed_ver1.cpp:13-232, compiled from the reference source) reaches the oracle's optimum."""
+import os
+import re
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INC = os.path.join(ROOT, "include")
+LIBDIR = os.path.join(ROOT, "cugp_b200")
+OUT = os.path.join(ROOT, "oracle", "_ref", "drivers")
+REF = "/root/reference"
+
+
+def _gxx(args, cwd=None):
+    r = subprocess.run(["g++", "-O2", "-w", *args], capture_output=True, text=True, cwd=cwd)
+    assert r.returncode == 0, r.stderr[-4000:]
+
+
+def _link_flags():
+    return ["-L" + LIBDIR, "-lcugp", "-Wl,-rpath," + LIBDIR]
+
+
+def _ensure_lib():
+    from cugp_b200 import build
+    build.build()
+
+
+def _build_probe():
+    _ensure_lib()
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, "shim_probe")
+    _gxx(["-I" + INC, os.path.join(ROOT, "tests", "shim", "shim_probe.cpp"), "-o", exe, *_link_flags()])
+    return exe
+
+
+def test_shim_probe_compiles_and_links():
+    exe = _build_probe()
+    assert os.path.exists(exe)
+    # every undefined cugp_* symbol of the binary is exported by the library
+    need = {l.split()[-1] for l in subprocess.run(["nm", "-u", exe], capture_output=True, text=True).stdout.splitlines()
+            if "cugp_" in l}
+    have = {l.split()[-1] for l in subprocess.run(["nm", "-D", "--defined-only", os.path.join(LIBDIR, "libcugp.so")],
+                                                  capture_output=True, text=True).stdout.splitlines()}
+    assert need and need <= have, need - have
+
+
+def test_header_symbols_exported():
+    """The C-ABI library exports every function include/cugp.h declares (no compute calls here)."""
+    _ensure_lib()
+    hdr = open(os.path.join(INC, "cugp.h")).read()
+    declared = set(re.findall(r"\b(cugp_[A-Za-z0-9_]+)\s*\(", hdr)) - {"cugp_eval_fn"}
+    have = {l.split()[-1] for l in subprocess.run(["nm", "-D", "--defined-only", os.path.join(LIBDIR, "libcugp.so")],
+                                                  capture_output=True, text=True).stdout.splitlines()}
+    assert declared <= have, declared - have
+    from cugp_b200._lib import SIGNATURES
+    assert declared == set(SIGNATURES), declared ^ set(SIGNATURES)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources only exist in the build container")
+def test_reference_drivers_build_unchanged_against_shim():
+    _ensure_lib()
+    os.makedirs(OUT, exist_ok=True)
+    with tempfile.TemporaryDirectory() as t:
+        # the reference's directory layout, with its three headers replaced by one-line forwards to the shim
+        for d in ("common", "cpp_serial_gp", "distributed_gp"):
+            os.makedirs(os.path.join(t, d))
+        shutil.copy(os.path.join(REF, "common", "cycleTimer.h"), os.path.join(t, "common"))
+        shutil.copy(os.path.join(REF, "cpp_serial_gp", "serial_gp.cpp"), os.path.join(t, "cpp_serial_gp"))
+        shutil.copy(os.path.join(REF, "distributed_gp", "distributed_ver1.cpp"), os.path.join(t, "distributed_gp"))
+        open(os.path.join(t, "common", "matrixops.h"), "w").write('#include "cugp_shim/matrixops.h"\n')
+        for d in ("cpp_serial_gp", "distributed_gp"):
+            open(os.path.join(t, d, "covkernel.h"), "w").write('#include "cugp_shim/covkernel.h"\n')
+        open(os.path.join(t, "distributed_gp", "BCM.h"), "w").write('#include "cugp_shim/BCM.h"\n')
+        _gxx(["-I" + INC, "serial_gp.cpp", "-o", os.path.join(OUT, "serial_gp"), *_link_flags()],
+             cwd=os.path.join(t, "cpp_serial_gp"))
+        # unqualified isnan/isinf (distributed_ver1.cpp:96,102,129,163) need the same compat pre-include as the oracle build
+        _gxx(["-I" + INC, "-include", os.path.join(ROOT, "oracle", "ref_compat.h"), "distributed_ver1.cpp", "-o", os.path.join(OUT, "distributed_ver1"), *_link_flags()],
+             cwd=os.path.join(t, "distributed_gp"))
+    assert os.path.exists(os.path.join(OUT, "serial_gp")) and os.path.exists(os.path.join(OUT, "distributed_ver1"))
+
+
+def _run(exe, cwd=None, timeout=600):
+    env = dict(os.environ, LD_LIBRARY_PATH=LIBDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([exe], capture_output=True, text=True, cwd=cwd, env=env, timeout=timeout)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    return r.stdout
+
+
+@pytest.mark.gpu
+def test_shim_probe_runs_and_matches_python_mirror():
+    import cugp_b200 as cg
+    exe = os.path.join(OUT, "shim_probe")
+    if not os.path.exists(exe):
+        exe = _build_probe()
+    out = _run(exe)
+    val = {l.split()[0]: [float(x) for x in re.findall(r"-?\d+\.?\d*(?:e[-+]?\d+)?|nan|inf", l.split(None, 1)[1])]
+           for l in out.splitlines() if l and l.split()[0].isupper()}
+    # same data as shim_probe.cpp
+    n, d, m = 96, 2, 8
+    s, X = 12345, np.zeros((n + m, d))
+    for i in range(n + m):
+        for j in range(d):
+            s = (s * 1664525 + 1013904223) & 0xFFFFFFFF
+            X[i, j] = -5.0 + 10.0 * (s >> 8) / 16777216.0
+    y = np.sin(X[:, 0])
+    th = [0.5, 0.25, -1.5]
+    g = cg.Covsum(n, d)
+    g.set_loghyperparam(th)
+    assert val["LL"][0] == g.compute_loglikelihood(X[:n], y[:n])
+    assert np.array_equal(val["GRAD"], g.compute_gradient_loghyperparam(X[:n], y[:n]))
+    mu, var = g.compute_test_means_and_variances(X[:n], y[:n], X[n:])
+    assert val["PRED"] == [mu[0], var[0]]
+    assert val["CHOLDET"][2] < 1e-9          # forward + backward matrix substitution reproduce compute_K_inverse
+    assert val["HOST"][0] < 1e-20            # K^-1 y (host helper on the GPU inverse) equals alpha
+    b = cg.BCM(X[:n], y[:n], K=3, rank=0, world=1)
+    b.set_BCM_log_hyperparam(th)
+    bll, bg = b.loglik_and_gradient()
+    assert val["BCM"][0] == bll and np.array_equal(val["BCM"][1:4], bg)
+    assert val["BCM"][-1] == 3 * th[0]
+    assert np.isfinite(val["CG"]).all() and np.isfinite(val["RPROP"]).all()
+
+
+@pytest.mark.gpu
+def test_reference_bcm_driver_runs_on_the_shim():
+    """distributed_gp/distributed_ver1.cpp, compiled unchanged: 128 x 2 points, 4 experts, theta0 = 1.5, its own
+    Polack-Ribiere loop.  Its final hyper-parameters ("PLEASE-SEE  3") must be the CPU oracle's to the 6 printed
+    digits."""
+    exe = os.path.join(OUT, "distributed_ver1")
+    if not os.path.exists(exe):
+        pytest.skip("driver binary not built (needs the reference sources; built in the CPU container)")
+    from oracle import oracle
+    from tests.conftest import load_data
+    d = load_data("si128x2")
+    with tempfile.TemporaryDirectory() as t:
+        os.makedirs(os.path.join(t, "dataset"))
+        os.makedirs(os.path.join(t, "run"))
+        with open(os.path.join(t, "dataset", "input_128.txt"), "w") as f:
+            f.write("128 2\n")
+            for row in d["X"]:
+                f.write(" ".join(repr(float(v)) for v in row) + "\n")
+        with open(os.path.join(t, "dataset", "label_128.txt"), "w") as f:
+            for v in d["y"]:
+                f.write(repr(float(v)) + "\n")
+        out = _run(exe, cwd=os.path.join(t, "run"))
+    finals = re.findall(r"PLEASE-SEE\s+3:\s*(\S+), (\S+), (\S+)", out)
+    assert finals, out[-2000:]
+    got = [float(v) for v in finals[-1]]
+    th, _ = oracle.port().cg_solve(d["X"], d["y"], [1.5, 1.5, 1.5], K=4)
+    assert [f"{v:.6f}" for v in got] == [f"{v:.6f}" for v in th], (got, th)
