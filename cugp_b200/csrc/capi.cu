@@ -770,6 +770,29 @@ int cugp_debug_gemm(const double* A, const double* B, double* C, int M, int N, i
     return CUGP_OK;
     CUGP_CATCH
 }
+int cugp_debug_diag_phases(const double* A128, long long* stamps, int nstamps) {
+    CUGP_TRY
+    if (int rc = require_device()) return rc;
+    if (!A128 || !stamps || nstamps < 20) return CUGP_ERR_INVALID;
+    double *dA = nullptr, *dInv = nullptr, *dLd = nullptr;
+    long long* dS = nullptr;
+    CUGP_CUDA(cudaMalloc((void**)&dA, 128 * 128 * 8));
+    CUGP_CUDA(cudaMalloc((void**)&dInv, 128 * 128 * 8));
+    CUGP_CUDA(cudaMalloc((void**)&dLd, 8));
+    CUGP_CUDA(cudaMalloc((void**)&dS, 32 * 8));
+    CUGP_CUDA(cudaMemset(dS, 0, 32 * 8));
+    for (int rep = 0; rep < 2; rep++) {  // second run: warm instruction cache
+        CUGP_CUDA(cudaMemcpy(dA, A128, 128 * 128 * 8, cudaMemcpyHostToDevice));
+        debug_diag_phases(dA, 128, 128, dInv, dLd, dS, 0);
+        CUGP_CUDA(cudaDeviceSynchronize());
+    }
+    long long h[32];
+    CUGP_CUDA(cudaMemcpy(h, dS, 32 * 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nstamps && i < 32; i++) stamps[i] = h[i];
+    cudaFree(dA); cudaFree(dInv); cudaFree(dLd); cudaFree(dS);
+    return CUGP_OK;
+    CUGP_CATCH
+}
 int cugp_probe_copy(size_t bytes, int iters, double* gbs) {
     CUGP_TRY
     if (int rc = require_device()) return rc;

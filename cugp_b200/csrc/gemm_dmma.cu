@@ -208,6 +208,36 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) dgemm_dmma_kernel(co
 
     double* __restrict__ C = p.C + offC;
     const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const bool interior = vec_ok && (m0 + BM <= p.M) && (n0 + BN <= p.N);
+    if (interior) {
+        // All loads of a batch are issued before the first use: one L2 round trip per batch instead of one per
+        // element pair (a load placed after a store to the same array cannot be hoisted by the compiler).
+        constexpr int IB = MI >= 4 ? 4 : MI;
+        double* base = C + (int64_t)(m0 + wm0 + g) * p.ldc + n0 + wn0 + 2 * q;
+#pragma unroll
+        for (int i0 = 0; i0 < MI; i0 += IB) {
+            double2 old[IB][NI];
+            if (p.beta != 0.0) {
+#pragma unroll
+                for (int i = 0; i < IB; i++)
+#pragma unroll
+                    for (int j = 0; j < NI; j++)
+                        old[i][j] = *reinterpret_cast<const double2*>(base + (int64_t)(i0 + i) * 8 * p.ldc + j * 8);
+            }
+#pragma unroll
+            for (int i = 0; i < IB; i++)
+#pragma unroll
+                for (int j = 0; j < NI; j++) {
+                    double v0 = p.alpha * acc[i0 + i][j][0], v1 = p.alpha * acc[i0 + i][j][1];
+                    if (p.beta != 0.0) {
+                        v0 += p.beta * old[i][j].x;
+                        v1 += p.beta * old[i][j].y;
+                    }
+                    *reinterpret_cast<double2*>(base + (int64_t)(i0 + i) * 8 * p.ldc + j * 8) = make_double2(v0, v1);
+                }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < MI; i++) {
         int row = m0 + wm0 + i * 8 + g;
@@ -319,7 +349,7 @@ __device__ __forceinline__ void raster_tile(int x, int tm, int tn, bool lower, i
     }
 }
 
-constexpr int NPW = 1;         // producer warps
+constexpr int NPW = 4;         // producer warps: a full warp group, so setmaxnreg can hand its registers to the math warps
 
 __device__ __forceinline__ void cp_async_arrive_noinc(unsigned long long* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -349,18 +379,18 @@ __device__ __forceinline__ void produce_operand(double* smem, const double* __re
         }
     } else {
         constexpr int CH = ROWS / 2;         // 16-byte chunks per k-row
-        constexpr int PER = CH / NL;         // chunks of one k-row per lane (CH >= NL for ROWS >= 64, NPW = 1)
-        static_assert(CH % NL == 0, "producer lanes must tile a k-row");
-#pragma unroll 2
-        for (int kr = 0; kr < WBK; kr++) {
-            const int gk = k0 + kr;
-#pragma unroll
-            for (int u = 0; u < PER; u++) {
-                const int mc = (pl + u * NL) * 2;
-                int nb = 0;
-                if (gk < k_hi) nb = min(max((rows_total - (row0 + mc)) * 8, 0), 16);
-                cp_async16(smem + kr * (ROWS + WPAD) + mc, nb ? g + (int64_t)gk * ld + row0 + mc : g, nb);
-            }
+        static_assert(NL % CH == 0, "producer lanes must cover whole k-rows");
+        constexpr int KSTEP = NL / CH;       // k-rows advanced per iteration
+        const int mc = (pl % CH) * 2, kr0 = pl / CH;
+        const int rowbytes = min(max((rows_total - (row0 + mc)) * 8, 0), 16);
+        const double* src = g + (int64_t)(k0 + kr0) * ld + row0 + mc;
+        double* dst = smem + kr0 * (ROWS + WPAD) + mc;
+#pragma unroll 4
+        for (int kr = kr0; kr < WBK; kr += KSTEP) {
+            const int nb = (k0 + kr < k_hi) ? rowbytes : 0;
+            cp_async16(dst, nb ? src : g, nb);
+            src += (int64_t)KSTEP * ld;
+            dst += KSTEP * (ROWS + WPAD);
         }
     }
 }
@@ -414,8 +444,12 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
     }
     __syncthreads();
 
+    // Register file split for the 12-warp configurations (168 registers each at launch): the producer warp group
+    // shrinks to 40 registers and the two math warp groups grow to 232 (12 * 168 = 4 * 40 + 8 * 232).
+    constexpr bool kRegSplit = (NCW == 8 && NPW == 4);
     if (warp >= NCW) {
         // ------------------------------ producer warp(s) ------------------------------
+        if (kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
         if (p.beta != 0.0 && !p.colsumsq) {  // pull the C tile into L2 while the main loop runs
             const double* C = p.C + offC;
             const int rows = min(BM, p.M - m0), cols = min(BN, p.N - n0);
@@ -438,6 +472,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
     }
 
     // ------------------------------ consumer warps ------------------------------
+    if (kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     const int g = lane >> 2, q = lane & 3;
     const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
     double acc[MI][NI][2];
@@ -510,6 +545,36 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
 
     double* __restrict__ C = p.C + offC;
     const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const bool interior = vec_ok && (m0 + BM <= p.M) && (n0 + BN <= p.N);
+    if (interior) {
+        // All loads of a batch are issued before the first use: one L2 round trip per batch instead of one per
+        // element pair (a load placed after a store to the same array cannot be hoisted by the compiler).
+        constexpr int IB = MI >= 4 ? 4 : MI;
+        double* base = C + (int64_t)(m0 + wm0 + g) * p.ldc + n0 + wn0 + 2 * q;
+#pragma unroll
+        for (int i0 = 0; i0 < MI; i0 += IB) {
+            double2 old[IB][NI];
+            if (p.beta != 0.0) {
+#pragma unroll
+                for (int i = 0; i < IB; i++)
+#pragma unroll
+                    for (int j = 0; j < NI; j++)
+                        old[i][j] = *reinterpret_cast<const double2*>(base + (int64_t)(i0 + i) * 8 * p.ldc + j * 8);
+            }
+#pragma unroll
+            for (int i = 0; i < IB; i++)
+#pragma unroll
+                for (int j = 0; j < NI; j++) {
+                    double v0 = p.alpha * acc[i0 + i][j][0], v1 = p.alpha * acc[i0 + i][j][1];
+                    if (p.beta != 0.0) {
+                        v0 += p.beta * old[i][j].x;
+                        v1 += p.beta * old[i][j].y;
+                    }
+                    *reinterpret_cast<double2*>(base + (int64_t)(i0 + i) * 8 * p.ldc + j * 8) = make_double2(v0, v1);
+                }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < MI; i++) {
         int row = m0 + wm0 + i * 8 + g;

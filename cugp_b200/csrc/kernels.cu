@@ -437,7 +437,7 @@ __device__ __forceinline__ void cta_gemm8(int mb, int nbk, bool lower, FA A, FB 
 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
     potrf_diag_blocked_kernel(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd,
-                              double* logdet_part, int nblk, int blk, int factor) {
+                              double* logdet_part, int nblk, int blk, int factor, long long* prof) {
     extern __shared__ __align__(16) double S[];
     double* tmp = S + DB * DLD;                // [64][TLD]
     double* rdiag = tmp + 64 * TLD;            // [128] reciprocals of L's diagonal
@@ -448,6 +448,13 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
     const int64_t b = blockIdx.x;
     double* Ab = A + b * sA + (int64_t)j0 * ld + j0;
     const int nb = min(DB, n - j0);
+    int stamp = 0;
+#define DIAG_STAMP()                                                \
+    do {                                                            \
+        if (prof && tid == 0 && blockIdx.x == 0) prof[stamp] = clock64(); \
+        stamp++;                                                    \
+    } while (0)
+    DIAG_STAMP();
 
     for (int e = tid; e < DB * DLD; e += DIAG_THREADS) {
         int i = e / DLD, j = e % DLD;
@@ -459,6 +466,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
         S[e] = v;
     }
     __syncthreads();
+    DIAG_STAMP();
 
     if (!factor) {  // the block already holds a triangular factor: only its inverse is wanted
         if (tid < DB) rdiag[tid] = 1.0 / S[tid * DLD + tid];
@@ -500,6 +508,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
                 if (c <= lane) S[(c0 + lane) * DLD + c0 + c] = a[c];
         }
         __syncthreads();
+        DIAG_STAMP();
         const int r0 = c0 + SB, m = DB - r0;
         if (m <= 0) break;
         // rows below: X L11^T = A21 by forward substitution, one thread per row (matrixops.cpp:330-340 transposed)
@@ -519,6 +528,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
             for (int c = 0; c < SB; c++) S[r * DLD + c0 + c] = a[c];
         }
         __syncthreads();
+        DIAG_STAMP();
         // trailing block of the diagonal block: A22 -= L21 L21^T (lower 8x8 blocks), K = 32
         cta_gemm8(
             m / 8, m / 8, true, [&](int i, int k) { return S[(r0 + i) * DLD + c0 + k]; },
@@ -531,9 +541,12 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
             },
             warp, NW, lane);
         __syncthreads();
+        DIAG_STAMP();
     }
 
     // ---------------- inverse ----------------
+    stamp = 11;
+    DIAG_STAMP();
     // diagonal 32x32 blocks: lane c solves L x = e_c (matrixops.cpp:330-340), 4 warps = 4 blocks
     if (warp < DB / SB) {
         const int c0 = warp * SB;
@@ -552,6 +565,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
             if (k >= lane) S[(c0 + lane) * DLD + c0 + k + 1] = r[k];  // T(c0+k, c0+lane)
     }
     __syncthreads();
+    DIAG_STAMP();
     // off-diagonal blocks by doubling: T21 = -T22 (L21 T11)
     for (int h = SB; h < DB; h *= 2) {
         const int npairs = DB / (2 * h);
@@ -581,6 +595,7 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
                 warp, NW, lane);
             __syncthreads();
         }
+        DIAG_STAMP();
     }
 
     // write back: L11 with zeroed upper triangle, inv(L11) dense 128x128 (zero upper)
@@ -590,6 +605,8 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
         if (factor && i < nb && j < nb) Ab[(int64_t)i * ld + j] = (j <= i) ? S[i * DLD + j] : 0.0;
         inv[e] = (j <= i) ? S[j * DLD + i + 1] : 0.0;
     }
+    DIAG_STAMP();
+#undef DIAG_STAMP
     if (!logdet_part) return;
     if (tid < DB) red[tid] = log(S[tid * DLD + tid]);
     __syncthreads();
@@ -885,8 +902,16 @@ void launch_potrf_diag(double* A, int64_t ld, int64_t sA, int n, int j0, double*
             configured = true;
         }
         potrf_diag_blocked_kernel<<<batch, DIAG_THREADS, smem, st>>>(A, ld, sA, n, j0, invd + (int64_t)blk * DB * DB,
-                                                                     sInvd, logdet_part, nblk, blk, 1);
+                                                                     sInvd, logdet_part, nblk, blk, 1, nullptr);
     }
+    CUGP_CUDA(cudaGetLastError());
+}
+
+// Phase timestamps (clock64 of thread 0) of one diagonal-block factorisation: tuning aid, see tools/diag_phases.py.
+void debug_diag_phases(double* A, int64_t ld, int n, double* invd, double* logdet, long long* stamps_dev, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(DB * DLD + 64 * TLD + DB + 2 * SB + DB) * sizeof(double);
+    CUGP_CUDA(cudaFuncSetAttribute(potrf_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    potrf_diag_blocked_kernel<<<1, DIAG_THREADS, smem, st>>>(A, ld, 0, n, 0, invd, 0, logdet, 1, 0, 1, stamps_dev);
     CUGP_CUDA(cudaGetLastError());
 }
 
@@ -900,7 +925,7 @@ void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* i
     }
     for (int blk = 0; blk * DB < n; blk++)
         potrf_diag_blocked_kernel<<<batch, DIAG_THREADS, smem, st>>>(const_cast<double*>(L), ld, sL, n, blk * DB,
-                                                                     invd + (int64_t)blk * DB * DB, sInvd, nullptr, 0, blk, 0);
+                                                                     invd + (int64_t)blk * DB * DB, sInvd, nullptr, 0, blk, 0, nullptr);
     CUGP_CUDA(cudaGetLastError());
 }
 

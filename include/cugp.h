@@ -175,6 +175,10 @@ int cugp_probe_gemm(int M, int N, int K, int iters, double *tflops);
  *   [ceil(M/BM)][N] per-row-tile column sums of squares and C is left untouched. */
 int cugp_debug_gemm(const double *A, const double *B, double *C, int M, int N, int K, double alpha, double beta,
                     int a_kc, int b_kc, int flags, int config, double *colsumsq);
+/* Tuning aid: clock64 stamps of thread 0 at the phase boundaries of one 128x128 diagonal-block factorisation
+ * (stamps[0] start, [1] loaded, [2..10] (chol, trsm, syrk) per 32-column panel, [11..12] diagonal inverses,
+ * [13..14] inverse doubling levels, [15] written back); nstamps >= 20. */
+int cugp_debug_diag_phases(const double *A128, long long *stamps, int nstamps);
 /* device copy bandwidth (read + write bytes / s) over `bytes` bytes, GB/s */
 int cugp_probe_copy(size_t bytes, int iters, double *gbs);
 
