@@ -188,6 +188,7 @@ GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(
     dalloc(y, bn);
     dalloc(Kb, (size_t)B * n * ld);
     dalloc(invd, (size_t)B * nblk * kDiag * kDiag);
+    CUGP_CUDA(cudaMemsetAsync(invd, 0, (size_t)B * nblk * kDiag * kDiag * sizeof(double), st));  // upper triangles stay zero
     dalloc(logdet_part, (size_t)B * nblk);
     dalloc(work, bn);
     dalloc(z, bn);

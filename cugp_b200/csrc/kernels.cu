@@ -403,35 +403,52 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// C(i,j) = sum_k A(i,k) B(k,j) over 8x8 output blocks, one block per warp at a time.  `lower`: only blocks
-// with bi >= bj of an mb x mb block grid.  krange(i0, j0, klo, khi) gives the k interval (multiples of 4).
+// C(i,j) = sum_k A(i,k) B(k,j) over 8x8 output blocks, one block per warp at a time (mb, nbk: counts of 8-blocks,
+// both even).  The 8 rows (columns) of a block are an interleaved half of a 16-row group,
+//     idx(b, g) = 16*(b/2) + 2*(b&1) + 4*(g&3) + (g>>2),
+// so that with the odd row strides used here (129, 65) the 8-byte fragment loads of a half-warp fall in 16
+// distinct bank pairs; with 8 consecutive rows they collide 4 ways and shared-memory bandwidth, not the DMMA
+// pipe, bounds these small products.  `lower`: only blocks whose 16-group satisfies gi >= gj; the store sees
+// real coordinates and masks j <= i itself.  krange(i16, j16, klo, khi) gives the k interval (multiples of 4)
+// for the 16-groups starting at i16 / j16.  k is split over 8 independent accumulator chains: a dependent DMMA
+// costs a few hundred clocks.
+__device__ __forceinline__ int frag_idx(int b, int g) { return 16 * (b >> 1) + 2 * (b & 1) + 4 * (g & 3) + (g >> 2); }
+
 template <class FA, class FB, class FK, class FS>
 __device__ __forceinline__ void cta_gemm8(int mb, int nbk, bool lower, FA A, FB B, FK krange, FS store, int warp,
                                           int nwarps, int lane) {
     const int g = lane >> 2, q = lane & 3;
-    const int nblocks = lower ? mb * (mb + 1) / 2 : mb * nbk;
-    for (int x = warp; x < nblocks; x += nwarps) {
-        int bi, bj;
+    const int mg = mb >> 1, ng = nbk >> 1;  // 16-groups
+    const int ngroups = lower ? mg * (mg + 1) / 2 : mg * ng;
+    for (int x = warp; x < ngroups * 4; x += nwarps) {
+        const int xg = x >> 2;
+        int gi, gj;
         if (lower) {
-            bi = (int)((sqrtf(8.f * (float)x + 1.f) - 1.f) * 0.5f);
-            while ((bi + 1) * (bi + 2) / 2 <= x) bi++;
-            while (bi * (bi + 1) / 2 > x) bi--;
-            bj = x - bi * (bi + 1) / 2;
+            gi = (int)((sqrtf(8.f * (float)xg + 1.f) - 1.f) * 0.5f);
+            while ((gi + 1) * (gi + 2) / 2 <= xg) gi++;
+            while (gi * (gi + 1) / 2 > xg) gi--;
+            gj = xg - gi * (gi + 1) / 2;
         } else {
-            bi = x / nbk;
-            bj = x % nbk;
+            gi = xg / ng;
+            gj = xg % ng;
         }
-        const int i0 = bi * 8, j0 = bj * 8;
+        const int bi = 2 * gi + ((x >> 1) & 1), bj = 2 * gj + (x & 1);
+        const int ia = frag_idx(bi, g);                                  // A-fragment row of this lane
+        const int jb = frag_idx(bj, g);                                  // B-fragment column of this lane
         int klo, khi;
-        krange(i0, j0, klo, khi);
-        double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;  // two accumulator chains
-        int k = klo;
-        for (; k + 8 <= khi; k += 8) {
-            dmma884(c0, c1, A(i0 + g, k + q), B(k + q, j0 + g));
-            dmma884(e0, e1, A(i0 + g, k + 4 + q), B(k + 4 + q, j0 + g));
+        krange(16 * gi, 16 * gj, klo, khi);
+        double c[8][2];
+#pragma unroll
+        for (int u = 0; u < 8; u++) c[u][0] = c[u][1] = 0.0;
+        for (int k = klo; k < khi; k += 32) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (k + 4 * u < khi) dmma884(c[u][0], c[u][1], A(ia, k + 4 * u + q), B(k + 4 * u + q, jb));
         }
-        if (k < khi) dmma884(c0, c1, A(i0 + g, k + q), B(k + q, j0 + g));
-        store(i0 + g, j0 + 2 * q, c0 + e0, c1 + e1);
+        const double c0 = ((c[0][0] + c[1][0]) + (c[2][0] + c[3][0])) + ((c[4][0] + c[5][0]) + (c[6][0] + c[7][0]));
+        const double c1 = ((c[0][1] + c[1][1]) + (c[2][1] + c[3][1])) + ((c[4][1] + c[5][1]) + (c[6][1] + c[7][1]));
+        // accumulator (g, 2q) and (g, 2q+1): row idx(bi, g), columns idx(bj, 2q) and idx(bj, 2q+1)
+        store(ia, frag_idx(bj, 2 * q), frag_idx(bj, 2 * q + 1), c0, c1);
     }
 }
 
@@ -456,14 +473,28 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
     } while (0)
     DIAG_STAMP();
 
-    for (int e = tid; e < DB * DLD; e += DIAG_THREADS) {
-        int i = e / DLD, j = e % DLD;
-        double v = 0.0;
-        if (j <= i) {  // lower triangle of A, identity padded
-            if (i < nb) v = Ab[(int64_t)i * ld + j];
-            else if (i == j) v = 1.0;
+    {
+        // warp w owns rows w, w+16, ...; lane owns columns lane + 32c: all 32 loads of a thread are in flight together
+        double v[DB / NW][4];
+#pragma unroll
+        for (int rr = 0; rr < DB / NW; rr++) {
+            const int i = warp + NW * rr;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int j = lane + 32 * c;
+                v[rr][c] = (j <= i && i < nb) ? Ab[(int64_t)i * ld + j] : 0.0;
+            }
         }
-        S[e] = v;
+#pragma unroll
+        for (int rr = 0; rr < DB / NW; rr++) {
+            const int i = warp + NW * rr;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int j = lane + 32 * c;
+                S[i * DLD + j] = (i >= nb && i == j) ? 1.0 : v[rr][c];  // lower triangle of A, identity padded
+            }
+            if (lane == 0) S[i * DLD + DB] = 0.0;
+        }
     }
     __syncthreads();
     DIAG_STAMP();
@@ -482,8 +513,8 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
 #pragma unroll
             for (int j = 0; j < SB; j++) {
                 const double ajj = __shfl_sync(0xffffffffu, a[j], j);
-                const double d = sqrt(ajj);          // negative pivot -> NaN, propagates (matrixops.cpp:77)
-                const double rd = 1.0 / d;
+                const double rd = rsqrt(ajj);        // negative pivot -> NaN, propagates (matrixops.cpp:77)
+                const double d = ajj * rd;           // sqrt(ajj) to 2 ulp without the sqrt -> divide latency chain
                 const double l = (lane == j) ? d : a[j] * rd;   // lanes < j hold 0
                 a[j] = l;
                 if (lane == j) rdiag[c0 + j] = rd;
@@ -534,10 +565,10 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
             m / 8, m / 8, true, [&](int i, int k) { return S[(r0 + i) * DLD + c0 + k]; },
             [&](int k, int j) { return S[(r0 + j) * DLD + c0 + k]; },
             [&](int, int, int& klo, int& khi) { klo = 0; khi = SB; },
-            [&](int i, int j, double v0, double v1) {
-                double* dst = S + (r0 + i) * DLD + r0 + j;
-                if (j <= i) dst[0] -= v0;
-                if (j + 1 <= i) dst[1] -= v1;
+            [&](int i, int ja, int jb, double v0, double v1) {
+                double* row = S + (r0 + i) * DLD + r0;
+                if (ja <= i) row[ja] -= v0;
+                if (jb <= i) row[jb] -= v1;
             },
             warp, NW, lane);
         __syncthreads();
@@ -577,9 +608,9 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
                 hb, hb, false, [&](int i, int k) { return S[(r2 + i) * DLD + r1 + k]; },
                 [&](int k, int j) { return k >= j ? S[(r1 + j) * DLD + r1 + k + 1] : 0.0; },
                 [&](int, int jj, int& klo, int& khi) { klo = jj; khi = h; },
-                [&](int i, int j, double v0, double v1) {
-                    tmp[i * TLD + j] = v0;
-                    tmp[i * TLD + j + 1] = v1;
+                [&](int i, int ja, int jb, double v0, double v1) {
+                    tmp[i * TLD + ja] = v0;
+                    tmp[i * TLD + jb] = v1;
                 },
                 warp, NW, lane);
             __syncthreads();
@@ -587,10 +618,10 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
             cta_gemm8(
                 hb, hb, false, [&](int i, int k) { return k <= i ? S[(r2 + k) * DLD + r2 + i + 1] : 0.0; },
                 [&](int k, int j) { return tmp[k * TLD + j]; },
-                [&](int ii, int, int& klo, int& khi) { klo = 0; khi = ii + 8; },
-                [&](int i, int j, double v0, double v1) {
-                    S[(r1 + j) * DLD + r2 + i + 1] = -v0;       // T(r2+i, r1+j)
-                    S[(r1 + j + 1) * DLD + r2 + i + 1] = -v1;
+                [&](int ii, int, int& klo, int& khi) { klo = 0; khi = ii + 16; },
+                [&](int i, int ja, int jb, double v0, double v1) {
+                    S[(r1 + ja) * DLD + r2 + i + 1] = -v0;       // T(r2+i, r1+j)
+                    S[(r1 + jb) * DLD + r2 + i + 1] = -v1;
                 },
                 warp, NW, lane);
             __syncthreads();
@@ -600,10 +631,17 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
 
     // write back: L11 with zeroed upper triangle, inv(L11) dense 128x128 (zero upper)
     double* inv = invd + b * sInvd;
-    for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
-        int i = e / DB, j = e % DB;
-        if (factor && i < nb && j < nb) Ab[(int64_t)i * ld + j] = (j <= i) ? S[i * DLD + j] : 0.0;
-        inv[e] = (j <= i) ? S[j * DLD + i + 1] : 0.0;
+#pragma unroll
+    for (int rr = 0; rr < DB / NW; rr++) {
+        const int i = warp + NW * rr;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int j = lane + 32 * c;
+            if (j <= i) {  // upper triangles: invd is zeroed at allocation, L's is never read (exports mask it)
+                if (factor && i < nb) Ab[(int64_t)i * ld + j] = S[i * DLD + j];
+                inv[i * DB + j] = S[j * DLD + i + 1];
+            }
+        }
     }
     DIAG_STAMP();
 #undef DIAG_STAMP

@@ -157,5 +157,5 @@ def test_reference_bcm_driver_runs_on_the_shim():
     finals = re.findall(r"PLEASE-SEE\s+3:\s*(\S+), (\S+), (\S+)", out)
     assert finals, out[-2000:]
     got = [float(v) for v in finals[-1]]
-    th, _ = oracle.port().cg_solve(d["X"], d["y"], [1.5, 1.5, 1.5], K=4)
+    th, _, _ = oracle.port().cg_solve(d["X"], d["y"], [1.5, 1.5, 1.5], K=4)
     assert [f"{v:.6f}" for v in got] == [f"{v:.6f}" for v in th], (got, th)
