@@ -138,6 +138,10 @@ int cugp_set_tuning(const char* key, long value) {
         set_potrf_outer_width((int)value);
         return CUGP_OK;
     }
+    if (std::strcmp(key, "lookahead") == 0) {
+        set_lookahead(value != 0);
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "gemm_kernel") == 0) {
         set_gemm_variant(value != 0);
         return CUGP_OK;

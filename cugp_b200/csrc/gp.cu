@@ -39,6 +39,9 @@ static cudaEvent_t prof_event(GpBatch::Prof* prof) {
 // Outer block width of the two-level factorisation: the trailing update runs with K = outer width, so its
 // C tiles are read and written once per outer step instead of once per 128 columns (the K = 128 update is
 // bound by that traffic: 8 flop/B).  Small matrices keep narrow outer blocks so the update still fills the GPU.
+static int g_lookahead = 1;
+void set_lookahead(int v) { g_lookahead = v; }
+bool lookahead_enabled() { return g_lookahead != 0; }
 static int g_potrf_nb = 0;  // 0: by size; otherwise forced (cugp_set_tuning("potrf_nb", v) or CUGP_POTRF_NB)
 void set_potrf_outer_width(int nb) { g_potrf_nb = nb; }
 int potrf_outer_width(int n) {
@@ -54,66 +57,110 @@ int potrf_outer_width(int n) {
     return kDiag;
 }
 
-void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part, int batch,
-                   cudaStream_t st, long* launches, GpBatch::Prof* prof) {
-    if (prof && !prof->on) prof = nullptr;
-    const int nblk = cdiv(n, kDiag);
-    const int NB = potrf_outer_width(n);
-    for (int J0 = 0; J0 < n; J0 += NB) {
-        const int Jend = std::min(n, J0 + NB);
-        // ---- panel: right-looking over the 128-column blocks of [J0, Jend), full height, updates confined to the panel
-        for (int j0 = J0; j0 < Jend; j0 += kDiag) {
-            const int blk = j0 / kDiag;
-            launch_potrf_diag(A, ld, sA, n, j0, invd, sInvd, logdet_part, nblk, blk, batch, st);
-            if (launches) ++*launches;
-            const int r0 = j0 + kDiag;
-            const int m = n - r0;
-            if (m <= 0) break;
-            double* A21 = A + (int64_t)r0 * ld + j0;
-            // TRSM panel: L21 = A21 * inv(L11)^T, in place (each CTA owns whole rows of the panel).
-            GemmParams p{};
-            p.A = A21; p.lda = ld; p.sA = sA;
-            p.B = invd + (int64_t)blk * kDiag * kDiag; p.ldb = kDiag; p.sB = sInvd;
-            p.C = A21; p.ldc = ld; p.sC = sA;
-            p.M = m; p.N = kDiag; p.K = kDiag;
-            p.alpha = 1.0; p.beta = 0.0;
-            p.batch = batch;
-            launch_gemm(p, true, true, GEMM_TALL, st);
-            if (launches) ++*launches;
-            // remaining columns of the panel: A[r0:, r0:Jend] -= L21 L21[0:w]^T, lower trapezoid
-            const int w = Jend - r0;
-            if (w <= 0) continue;
-            GemmParams q{};
-            q.A = A21; q.lda = ld; q.sA = sA;
-            q.B = A21; q.ldb = ld; q.sB = sA;
-            q.C = A + (int64_t)r0 * (ld + 1); q.ldc = ld; q.sC = sA;
-            q.M = m; q.N = w; q.K = kDiag;
-            q.alpha = -1.0; q.beta = 1.0;
-            q.batch = batch;
-            q.lower_tiles = 1;
-            launch_gemm(q, true, true, pick_config(m, w, batch, true), st);
-            if (launches) ++*launches;
-        }
-        // ---- trailing update: A[Jend:, Jend:] -= P P^T with P = L[Jend:, J0:Jend], lower tiles, K = outer width
-        const int m = n - Jend;
-        if (m <= 0) continue;
+// One outer panel [J0, Jend): right-looking over its 128-column blocks, full height, updates confined to the panel.
+static void potrf_panel(double* A, int64_t ld, int64_t sA, int n, int J0, int Jend, double* invd, int64_t sInvd,
+                        double* logdet_part, int nblk, int batch, cudaStream_t st, long* launches) {
+    for (int j0 = J0; j0 < Jend; j0 += kDiag) {
+        const int blk = j0 / kDiag;
+        launch_potrf_diag(A, ld, sA, n, j0, invd, sInvd, logdet_part, nblk, blk, batch, st);
+        if (launches) ++*launches;
+        const int r0 = j0 + kDiag;
+        const int m = n - r0;
+        if (m <= 0) break;
+        double* A21 = A + (int64_t)r0 * ld + j0;
+        // TRSM panel: L21 = A21 * inv(L11)^T, in place (each CTA owns whole rows of the panel).
+        GemmParams p{};
+        p.A = A21; p.lda = ld; p.sA = sA;
+        p.B = invd + (int64_t)blk * kDiag * kDiag; p.ldb = kDiag; p.sB = sInvd;
+        p.C = A21; p.ldc = ld; p.sC = sA;
+        p.M = m; p.N = kDiag; p.K = kDiag;
+        p.alpha = 1.0; p.beta = 0.0;
+        p.batch = batch;
+        launch_gemm(p, true, true, GEMM_TALL, st);
+        if (launches) ++*launches;
+        // remaining columns of the panel: A[r0:, r0:Jend] -= L21 L21[0:w]^T, lower trapezoid
+        const int w = Jend - r0;
+        if (w <= 0) continue;
         GemmParams q{};
-        q.A = A + (int64_t)Jend * ld + J0; q.lda = ld; q.sA = sA;
-        q.B = q.A; q.ldb = ld; q.sB = sA;
-        q.C = A + (int64_t)Jend * (ld + 1); q.ldc = ld; q.sC = sA;
-        q.M = m; q.N = m; q.K = Jend - J0;
+        q.A = A21; q.lda = ld; q.sA = sA;
+        q.B = A21; q.ldb = ld; q.sB = sA;
+        q.C = A + (int64_t)r0 * (ld + 1); q.ldc = ld; q.sC = sA;
+        q.M = m; q.N = w; q.K = kDiag;
         q.alpha = -1.0; q.beta = 1.0;
         q.batch = batch;
         q.lower_tiles = 1;
-        if (prof) CUGP_CUDA(cudaEventRecord(prof_event(prof), st));
-        launch_gemm(q, true, true, pick_config(m, m, batch, true), st);
-        if (prof) {
-            CUGP_CUDA(cudaEventRecord(prof_event(prof), st));
-            prof->flops += (double)batch * (double)m * ((double)m + 1.0) * (double)(Jend - J0);  // lower triangle, 2 flop per MAC
-            prof->count++;
-        }
+        launch_gemm(q, true, true, pick_config(m, w, batch, true), st);
         if (launches) ++*launches;
     }
+}
+
+// A[c0:, c0:c1] -= P[c0:, :] P[c0:c1, :]^T with P = L[:, J0:Jend] (lower trapezoid; c1 == n: the whole trailing block)
+static void potrf_trailing(double* A, int64_t ld, int64_t sA, int n, int J0, int Jend, int c0, int c1, int batch,
+                           cudaStream_t st, long* launches, GpBatch::Prof* prof) {
+    const int m = n - c0, w = c1 - c0;
+    if (m <= 0 || w <= 0) return;
+    GemmParams q{};
+    q.A = A + (int64_t)c0 * ld + J0; q.lda = ld; q.sA = sA;
+    q.B = q.A; q.ldb = ld; q.sB = sA;
+    q.C = A + (int64_t)c0 * (ld + 1); q.ldc = ld; q.sC = sA;
+    q.M = m; q.N = w; q.K = Jend - J0;
+    q.alpha = -1.0; q.beta = 1.0;
+    q.batch = batch;
+    q.lower_tiles = 1;
+    if (prof) CUGP_CUDA(cudaEventRecord(prof_event(prof), st));
+    launch_gemm(q, true, true, pick_config(m, w, batch, true), st);
+    if (prof) {
+        CUGP_CUDA(cudaEventRecord(prof_event(prof), st));
+        // lower trapezoid, 2 flop per MAC: w(w+1)/2 + (m-w)w outputs
+        prof->flops += (double)batch * 2.0 * ((double)w * (w + 1.0) / 2.0 + (double)(m - w) * w) * (double)(Jend - J0);
+        prof->count++;
+    }
+    if (launches) ++*launches;
+}
+
+void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part, int batch,
+                   cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la) {
+    if (prof && !prof->on) prof = nullptr;
+    const int nblk = cdiv(n, kDiag);
+    const int NB = potrf_outer_width(n);
+    const int npanels = cdiv(n, NB);
+    if (!la || !la->st2 || npanels < 3 || !lookahead_enabled()) {
+        for (int J0 = 0; J0 < n; J0 += NB) {
+            const int Jend = std::min(n, J0 + NB);
+            potrf_panel(A, ld, sA, n, J0, Jend, invd, sInvd, logdet_part, nblk, batch, st, launches);
+            // trailing update: A[Jend:, Jend:] -= P P^T with P = L[Jend:, J0:Jend], lower tiles, K = outer width
+            potrf_trailing(A, ld, sA, n, J0, Jend, Jend, n, batch, st, launches, prof);
+        }
+        return;
+    }
+    // Look-ahead of one panel: the panel stream (high priority) factors panel J+1 while the main stream applies the
+    // bulk of panel J's trailing update.  The update of panel J is split at the next panel's right edge:
+    //   U1(J) = columns of panel J+1 (panel stream, on the critical path),  U2(J) = everything right of it (main stream).
+    // Both U1(J) and U2(J-1) write the columns of panel J+1, so U1(J) waits for U2(J-1).
+    cudaStream_t s2 = la->st2;
+    while ((int)la->ev.size() < 2 * npanels + 2) {
+        cudaEvent_t e;
+        CUGP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        la->ev.push_back(e);
+    }
+    auto evP = [&](int J) { return la->ev[2 * J]; };
+    auto evU = [&](int J) { return la->ev[2 * J + 1]; };
+    cudaEvent_t ev_start = la->ev[2 * npanels], ev_end = la->ev[2 * npanels + 1];
+    CUGP_CUDA(cudaEventRecord(ev_start, st));          // K is complete on the main stream
+    CUGP_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
+    for (int J = 0; J < npanels; J++) {
+        const int J0 = J * NB, Jend = std::min(n, J0 + NB), Jend2 = std::min(n, Jend + NB);
+        potrf_panel(A, ld, sA, n, J0, Jend, invd, sInvd, logdet_part, nblk, batch, s2, launches);
+        CUGP_CUDA(cudaEventRecord(evP(J), s2));
+        if (Jend >= n) break;
+        if (J >= 1) CUGP_CUDA(cudaStreamWaitEvent(s2, evU(J - 1), 0));
+        potrf_trailing(A, ld, sA, n, J0, Jend, Jend, Jend2, batch, s2, launches, nullptr);   // U1(J)
+        CUGP_CUDA(cudaStreamWaitEvent(st, evP(J), 0));
+        potrf_trailing(A, ld, sA, n, J0, Jend, Jend2, n, batch, st, launches, prof);          // U2(J)
+        CUGP_CUDA(cudaEventRecord(evU(J), st));
+    }
+    CUGP_CUDA(cudaEventRecord(ev_end, s2));
+    CUGP_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
 }
 
 void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t sM, int n, const double* invd,
@@ -183,6 +230,11 @@ GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(
         CUGP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         own_stream = true;
     }
+    {
+        int lo = 0, hi = 0;  // the panel stream of the look-ahead Cholesky gets the highest priority
+        CUGP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUGP_CUDA(cudaStreamCreateWithPriority(&la.st2, cudaStreamNonBlocking, hi));
+    }
     const size_t bn = (size_t)B * n;
     dalloc(X, bn * dp);
     dalloc(y, bn);
@@ -204,6 +256,11 @@ GpBatch::~GpBatch() {
     dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar);
     if (hstage) cudaFreeHost(hstage);
     for (cudaEvent_t e : prof.ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : la.ev) cudaEventDestroy(e);
+    if (la.st2) {
+        cudaStreamSynchronize(la.st2);
+        cudaStreamDestroy(la.st2);
+    }
     if (own_stream && st) cudaStreamDestroy(st);
 }
 
@@ -252,7 +309,7 @@ void GpBatch::build_K(int full) {
 }
 
 void GpBatch::potrf() {
-    potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof);
+    potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la);
 }
 
 void GpBatch::prof_begin() {

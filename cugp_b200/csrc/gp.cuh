@@ -11,6 +11,12 @@
 
 namespace cugp {
 
+// Second stream + events of the look-ahead Cholesky (owned by a GpBatch).
+struct PotrfLookahead {
+    cudaStream_t st2 = nullptr;
+    std::vector<cudaEvent_t> ev;
+};
+
 struct GpBatch {
     int B = 0, n = 0, d = 0, dp = 0, nblk = 0;
     int64_t ld = 0;
@@ -45,6 +51,7 @@ struct GpBatch {
         double flops = 0.0;            // algorithmic flops of the bracketed launches
         long count = 0;
     } prof;
+    PotrfLookahead la;
     void prof_begin();                     // reset counters (events are reused)
     void prof_collect(double* ms, double* flops, long* count);
 
@@ -80,7 +87,9 @@ struct GpBatch {
 // Blocked right-looking Cholesky of `batch` matrices in place (lower), with the inverses of the
 // 128x128 diagonal blocks and per-block log-determinant partials as by-products.
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part,
-                   int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr);
+                   int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr, PotrfLookahead* la = nullptr);
+void set_lookahead(int v);  // 1 (default): factor panel J+1 on a second stream while panel J's trailing update runs
+bool lookahead_enabled();
 // Outer block width used for an n x n factorisation; set_potrf_outer_width(0) restores the size-based default.
 int potrf_outer_width(int n);
 void set_potrf_outer_width(int nb);

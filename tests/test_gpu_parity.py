@@ -126,6 +126,25 @@ def test_two_level_cholesky(n, nb):
     assert lib().cugp_set_tuning(b"potrf_nb", 100) != 0 and lib().cugp_set_tuning(b"nope", 1) != 0
 
 
+@pytest.mark.parametrize("n,nb", [(1000, 128), (1500, 256), (2100, 512)])
+def test_lookahead_is_bitwise_neutral(n, nb):
+    """Panel look-ahead only reorders independent launches across two streams: every C tile still receives the same
+    updates in the same order, so L is bit-identical with and without it."""
+    K, _ = _spd(n, 3 * n)
+    try:
+        lib().cugp_set_tuning(b"potrf_nb", nb)
+        lib().cugp_set_tuning(b"lookahead", 0)
+        L0 = cg.get_cholesky(K)
+        lib().cugp_set_tuning(b"lookahead", 1)
+        L1 = cg.get_cholesky(K)
+    finally:
+        lib().cugp_set_tuning(b"potrf_nb", 0)
+        lib().cugp_set_tuning(b"lookahead", 1)
+    assert np.array_equal(L0, L1)
+    Lo = PORT.cholesky(K)
+    assert np.linalg.norm(L1 - Lo) <= 1e-12 * np.linalg.norm(Lo)
+
+
 def test_non_pd_is_nan_not_an_error():
     """sqrt of a negative pivot gives NaN that propagates; status stays OK (matrixops.cpp:77)."""
     A = np.array([[1.0, 2.0], [2.0, 1.0]])
