@@ -313,7 +313,7 @@ int cugp_covsum_factorize_resident(cugp_covsum* h, float* ms_cov, float* ms_chol
     CUGP_CUDA(cudaEventRecord(e0, g.st));
     g.build_K(0);
     CUGP_CUDA(cudaEventRecord(e1, g.st));
-    g.potrf();
+    g.potrf_with_rhs();  // Cholesky with the fused forward substitution
     CUGP_CUDA(cudaEventRecord(e2, g.st));
     CUGP_CUDA(cudaEventSynchronize(e2));
     g.have_L = true;
@@ -442,7 +442,7 @@ static int solve_with_K(const double* K, const double* y, int n, double* quad, d
     std::vector<double> x0(n, 0.0);
     g.set_data(x0.data(), y);
     load_matrix(g, K);
-    g.potrf();
+    g.potrf_with_rhs();
     g.have_L = true;
     double s[4];
     g.scalars(s);

@@ -450,14 +450,6 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
     if (warp >= NCW) {
         // ------------------------------ producer warp(s) ------------------------------
         if (kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
-        if (p.beta != 0.0 && !p.colsumsq) {  // pull the C tile into L2 while the main loop runs
-            const double* C = p.C + offC;
-            const int rows = min(BM, p.M - m0), cols = min(BN, p.N - n0);
-            for (int r = lane; r < rows; r += 32) {
-                const double* row = C + (int64_t)(m0 + r) * p.ldc + n0;
-                for (int c = 0; c < cols; c += 16) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + c));
-            }
-        }
         const int pl = tid - NCW * 32;  // producer lane
         for (int kt = 0; kt < nk; kt++) {
             const int s = kt % NSTAGE;
@@ -466,6 +458,16 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
             produce_operand<BM, A_KC>(As + s * A_SZ, A, p.lda, m0, p.M, k0, k_hi, pl);
             produce_operand<BN, B_KC>(Bs + s * B_SZ, B, p.ldb, n0, p.N, k0, k_hi, pl);
             cp_async_arrive_noinc(&full[s]);  // this lane's arrival fires when its copies above have landed
+        }
+        if (p.beta != 0.0 && !p.colsumsq) {
+            // All stages are issued: pull the C tile into L2 now, NSTAGE stages ahead of the epilogue that reads it
+            // (prefetching at kernel start had the lines evicted again before use: DRAM read C twice).
+            const double* C = p.C + offC;
+            const int rows = min(BM, p.M - m0), cols = min(BN, p.N - n0);
+            for (int r = pl; r < rows; r += NPW * 32) {
+                const double* row = C + (int64_t)(m0 + r) * p.ldc + n0;
+                for (int c = 0; c < cols; c += 16) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + c));
+            }
         }
         cp_async_wait<0>();
         return;

@@ -58,14 +58,17 @@ int potrf_outer_width(int n) {
 }
 
 // One outer panel [J0, Jend): right-looking over its 128-column blocks, full height, updates confined to the panel.
-static void potrf_panel(double* A, int64_t ld, int64_t sA, int n, int J0, int Jend, double* invd, int64_t sInvd,
+// `nrows` >= n: rows n.. of A are appended right-hand sides (y^T): they ride through the TRSM and the updates like
+// any other row below the diagonal, which performs the forward substitution L z = y for free (z^T ends up in row n).
+static void potrf_panel(double* A, int64_t ld, int64_t sA, int n, int nrows, int J0, int Jend, double* invd, int64_t sInvd,
                         double* logdet_part, int nblk, int batch, cudaStream_t st, long* launches) {
     for (int j0 = J0; j0 < Jend; j0 += kDiag) {
         const int blk = j0 / kDiag;
         launch_potrf_diag(A, ld, sA, n, j0, invd, sInvd, logdet_part, nblk, blk, batch, st);
         if (launches) ++*launches;
-        const int r0 = j0 + kDiag;
-        const int m = n - r0;
+        const int nbk = std::min(kDiag, n - j0);  // < 128 only for the last block
+        const int r0 = j0 + nbk;
+        const int m = nrows - r0;
         if (m <= 0) break;
         double* A21 = A + (int64_t)r0 * ld + j0;
         // TRSM panel: L21 = A21 * inv(L11)^T, in place (each CTA owns whole rows of the panel).
@@ -73,7 +76,7 @@ static void potrf_panel(double* A, int64_t ld, int64_t sA, int n, int J0, int Je
         p.A = A21; p.lda = ld; p.sA = sA;
         p.B = invd + (int64_t)blk * kDiag * kDiag; p.ldb = kDiag; p.sB = sInvd;
         p.C = A21; p.ldc = ld; p.sC = sA;
-        p.M = m; p.N = kDiag; p.K = kDiag;
+        p.M = m; p.N = nbk; p.K = nbk;
         p.alpha = 1.0; p.beta = 0.0;
         p.batch = batch;
         launch_gemm(p, true, true, GEMM_TALL, st);
@@ -95,9 +98,9 @@ static void potrf_panel(double* A, int64_t ld, int64_t sA, int n, int J0, int Je
 }
 
 // A[c0:, c0:c1] -= P[c0:, :] P[c0:c1, :]^T with P = L[:, J0:Jend] (lower trapezoid; c1 == n: the whole trailing block)
-static void potrf_trailing(double* A, int64_t ld, int64_t sA, int n, int J0, int Jend, int c0, int c1, int batch,
+static void potrf_trailing(double* A, int64_t ld, int64_t sA, int nrows, int J0, int Jend, int c0, int c1, int batch,
                            cudaStream_t st, long* launches, GpBatch::Prof* prof) {
-    const int m = n - c0, w = c1 - c0;
+    const int m = nrows - c0, w = c1 - c0;
     if (m <= 0 || w <= 0) return;
     GemmParams q{};
     q.A = A + (int64_t)c0 * ld + J0; q.lda = ld; q.sA = sA;
@@ -119,17 +122,18 @@ static void potrf_trailing(double* A, int64_t ld, int64_t sA, int n, int J0, int
 }
 
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part, int batch,
-                   cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la) {
+                   cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la, int rhs_rows) {
     if (prof && !prof->on) prof = nullptr;
+    const int nrows = n + rhs_rows;
     const int nblk = cdiv(n, kDiag);
     const int NB = potrf_outer_width(n);
     const int npanels = cdiv(n, NB);
     if (!la || !la->st2 || npanels < 3 || !lookahead_enabled()) {
         for (int J0 = 0; J0 < n; J0 += NB) {
             const int Jend = std::min(n, J0 + NB);
-            potrf_panel(A, ld, sA, n, J0, Jend, invd, sInvd, logdet_part, nblk, batch, st, launches);
+            potrf_panel(A, ld, sA, n, nrows, J0, Jend, invd, sInvd, logdet_part, nblk, batch, st, launches);
             // trailing update: A[Jend:, Jend:] -= P P^T with P = L[Jend:, J0:Jend], lower tiles, K = outer width
-            potrf_trailing(A, ld, sA, n, J0, Jend, Jend, n, batch, st, launches, prof);
+            potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend, n, batch, st, launches, prof);
         }
         return;
     }
@@ -150,13 +154,13 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
     CUGP_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
     for (int J = 0; J < npanels; J++) {
         const int J0 = J * NB, Jend = std::min(n, J0 + NB), Jend2 = std::min(n, Jend + NB);
-        potrf_panel(A, ld, sA, n, J0, Jend, invd, sInvd, logdet_part, nblk, batch, s2, launches);
+        potrf_panel(A, ld, sA, n, nrows, J0, Jend, invd, sInvd, logdet_part, nblk, batch, s2, launches);
         CUGP_CUDA(cudaEventRecord(evP(J), s2));
         if (Jend >= n) break;
         if (J >= 1) CUGP_CUDA(cudaStreamWaitEvent(s2, evU(J - 1), 0));
-        potrf_trailing(A, ld, sA, n, J0, Jend, Jend, Jend2, batch, s2, launches, nullptr);   // U1(J)
+        potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend, Jend2, batch, s2, launches, nullptr);   // U1(J)
         CUGP_CUDA(cudaStreamWaitEvent(st, evP(J), 0));
-        potrf_trailing(A, ld, sA, n, J0, Jend, Jend2, n, batch, st, launches, prof);          // U2(J)
+        potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend2, n, batch, st, launches, prof);          // U2(J)
         CUGP_CUDA(cudaEventRecord(evU(J), st));
     }
     CUGP_CUDA(cudaEventRecord(ev_end, s2));
@@ -238,7 +242,7 @@ GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(
     const size_t bn = (size_t)B * n;
     dalloc(X, bn * dp);
     dalloc(y, bn);
-    dalloc(Kb, (size_t)B * n * ld);
+    dalloc(Kb, (size_t)B * (n + 1) * ld);  // row n of every matrix: y^T, then z^T = (L^-1 y)^T
     dalloc(invd, (size_t)B * nblk * kDiag * kDiag);
     CUGP_CUDA(cudaMemsetAsync(invd, 0, (size_t)B * nblk * kDiag * kDiag * sizeof(double), st));  // upper triangles stay zero
     dalloc(logdet_part, (size_t)B * nblk);
@@ -308,8 +312,19 @@ void GpBatch::build_K(int full) {
     launches++;
 }
 
-void GpBatch::potrf() {
-    potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la);
+void GpBatch::potrf(bool with_rhs) {
+    potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la,
+                  with_rhs ? 1 : 0);
+}
+
+// Cholesky of the matrix in Kb with y appended as row n: L in place, z = L^-1 y in row n, then
+// (quad = z'z = y'K^-1 y, logdet, LL) -- matrixops.cpp:113-185 + covkernel.cpp:127 without a separate forward sweep.
+void GpBatch::potrf_with_rhs() {
+    launch_copy_rows(y, n, Kb + (int64_t)n * ld, mat_stride(), n, B, st);
+    potrf(true);
+    const double* zrow = Kb + (int64_t)n * ld;
+    launch_ll_finalize(zrow, zrow, mat_stride(), n, logdet_part, nblk, scal, B, st);
+    launches += 2;
 }
 
 void GpBatch::prof_begin() {
@@ -334,25 +349,31 @@ void GpBatch::prof_collect(double* ms, double* flops, long* count) {
 void GpBatch::factorize() {
     if (have_L) return;
     build_K(0);
-    potrf();
+    potrf_with_rhs();
     have_L = true;
 }
 
+// alpha = L^-T z.  With T = L^-1 at hand (gradient / prediction paths) it is one streaming pass alpha = T^T z;
+// otherwise the blocked backward sweep over L (matrixops.cpp:156-164).
 void GpBatch::solve() {
     if (have_alpha) return;
     factorize();
-    const int64_t sI = (int64_t)nblk * kDiag * kDiag;
-    launch_copy_vec(y, work, (int64_t)B * n, st);
-    launch_trsv_forward(Kb, ld, mat_stride(), n, invd, sI, work, z, n, B, st);
-    launch_trsv_backward(Kb, ld, mat_stride(), n, invd, sI, z, alpha, n, B, st);  // z doubles as the work vector
-    launch_ll_finalize(y, alpha, n, n, logdet_part, nblk, scal, B, st);
-    launches += 2 + 2 * nblk;
+    const double* zrow = Kb + (int64_t)n * ld;
+    if (have_T) {
+        launch_gemv_t(Tb, ld, mat_stride(), n, zrow, mat_stride(), alpha, n, B, st);
+        launches += 1;
+    } else {
+        const int64_t sI = (int64_t)nblk * kDiag * kDiag;
+        launch_copy_rows(zrow, mat_stride(), work, n, n, B, st);  // the sweep consumes its right-hand side
+        launch_trsv_backward(Kb, ld, mat_stride(), n, invd, sI, work, alpha, n, B, st);
+        launches += 1 + nblk;
+    }
     have_alpha = true;
 }
 
 void GpBatch::ensure_TW() {
-    dalloc(Tb, (size_t)B * n * ld);
-    dalloc(Wb, (size_t)B * n * ld);
+    dalloc(Tb, (size_t)B * (n + 1) * ld);  // same batch stride as Kb
+    dalloc(Wb, (size_t)B * (n + 1) * ld);
 }
 
 void GpBatch::trtri() {
@@ -382,7 +403,7 @@ void GpBatch::lauum() {
 }
 
 void GpBatch::scalars(double* out4) {
-    solve();
+    factorize();
     CUGP_CUDA(cudaMemcpyAsync(out4, scal, (size_t)B * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     sync();
 }
@@ -394,6 +415,7 @@ void GpBatch::loglik(double* ll_out) {
 }
 
 void GpBatch::gradient(double* g_out) {
+    trtri();   // before solve(): alpha then is a single pass over T
     solve();
     lauum();
     dalloc(gradpart, grad_trace_partials(n, B));
@@ -428,8 +450,8 @@ void GpBatch::ensure_pred(int mc) {
 // mean_h/var_h: [B][m] host (may be null).  PQ_dev: [2][m] device product-of-experts moments (may be null).
 void GpBatch::predict(const double* Xt_h, int m, double* mean_h, double* var_h, double* PQ_dev, int accumulate) {
     if (m <= 0) return;
-    solve();
     trtri();
+    solve();
     // chunk the test set so Kstar stays near 2 GB
     int64_t cap = (int64_t)(2.0e9 / ((double)B * ld * 8.0));
     int mc = (int)std::min<int64_t>(m, std::max<int64_t>(64, cap / 64 * 64));

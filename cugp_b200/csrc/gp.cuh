@@ -25,7 +25,7 @@ struct GpBatch {
 
     // device buffers
     double *X = nullptr, *y = nullptr;      // [B][n][dp], [B][n]
-    double* Kb = nullptr;                   // [B][n][ld]: K, then L in place
+    double* Kb = nullptr;                   // [B][n+1][ld]: K, then L in place; row n: y^T, then z^T = (L^-1 y)^T
     double* invd = nullptr;                 // [B][nblk][128][128] inverses of L's diagonal blocks
     double* logdet_part = nullptr;          // [B][nblk]
     double *work = nullptr, *z = nullptr, *alpha = nullptr;  // [B][n]
@@ -66,9 +66,10 @@ struct GpBatch {
     void invalidate() { have_L = have_alpha = have_T = have_Kinv = false; }
 
     void build_K(int full);                 // K1 into Kb
-    void potrf();                           // K2 on Kb (expects K in the lower triangle)
+    void potrf(bool with_rhs = false);      // K2 on Kb (expects K in the lower triangle; with_rhs: row n rides along)
+    void potrf_with_rhs();                  // y -> row n, K2, then quad = z'z, logdet, LL into scal
     void factorize();                       // build_K + potrf (cached)
-    void solve();                           // + K3: alpha, quad, logdet, LL (cached)
+    void solve();                           // + K3: alpha = L^-T z (cached)
     void trtri();                           // T = L^-1 (cached)
     void lauum();                           // Kinv (lower) = T^T T into Wb (cached)
     void loglik(double* ll_out);            // [B] host
@@ -79,7 +80,7 @@ struct GpBatch {
 
     void sync() { CUGP_CUDA(cudaStreamSynchronize(st)); }
     void* stage(size_t bytes);
-    int64_t mat_stride() const { return (int64_t)n * ld; }
+    int64_t mat_stride() const { return (int64_t)(n + 1) * ld; }  // n rows + the appended right-hand-side row
     void ensure_TW();
     void ensure_pred(int mc);
 };
@@ -87,7 +88,8 @@ struct GpBatch {
 // Blocked right-looking Cholesky of `batch` matrices in place (lower), with the inverses of the
 // 128x128 diagonal blocks and per-block log-determinant partials as by-products.
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part,
-                   int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr, PotrfLookahead* la = nullptr);
+                   int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr, PotrfLookahead* la = nullptr,
+                   int rhs_rows = 0);
 void set_lookahead(int v);  // 1 (default): factor panel J+1 on a second stream while panel J's trailing update runs
 bool lookahead_enabled();
 // Outer block width used for an n x n factorisation; set_potrf_outer_width(0) restores the size-based default.

@@ -656,74 +656,14 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: triangular solves.  One launch per 128-column block; every CTA first recomputes the block's
+// K3: triangular solves.  The forward substitution L z = y is fused into the Cholesky (y^T is row n of the
+// matrix, see gp.cu).  alpha = L^-T z is either one streaming pass over T = L^-1 (gemv_t_kernel) or the
+// blocked backward sweep below: one launch per 128-row block; every CTA first recomputes the block's
 // solution with the stored inverse of the diagonal block (128x128 GEMV, L2 resident) and then applies
-// it to its own slice of the remaining right-hand side, so a sweep streams L exactly once.
+// it to its own slice of the remaining right-hand side, so the sweep streams L exactly once.
 // ------------------------------------------------------------------------------------------------
 constexpr int TRSV_THREADS = 256;
-constexpr int FWD_ROWS = 256;   // rows of the panel below handled per CTA
 constexpr int BWD_COLS = 512;   // columns of the block row handled per CTA
-
-__global__ void __launch_bounds__(TRSV_THREADS)
-    trsv_fwd_step_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int n, int j0,
-                         const double* __restrict__ invd, int64_t sInvd, double* work, double* z, int64_t sVec) {
-    __shared__ __align__(16) double rj[DB];
-    __shared__ __align__(16) double zj[DB];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t b = blockIdx.y;
-    L += b * sL;
-    invd += b * sInvd + (int64_t)(j0 / DB) * DB * DB;
-    work += b * sVec;
-    z += b * sVec;
-    const int nb = min(DB, n - j0);
-    if (tid < DB) rj[tid] = tid < nb ? work[j0 + tid] : 0.0;
-    __syncthreads();
-    // z_j = inv(L_jj) r_j
-    {
-        const double2 r0 = *reinterpret_cast<const double2*>(rj + lane * 4);
-        const double2 r1 = *reinterpret_cast<const double2*>(rj + lane * 4 + 2);
-#pragma unroll 4
-        for (int rr = 0; rr < DB / 8; rr++) {
-            int row = warp * (DB / 8) + rr;
-            const double2 a0 = *reinterpret_cast<const double2*>(invd + row * DB + lane * 4);
-            const double2 a1 = *reinterpret_cast<const double2*>(invd + row * DB + lane * 4 + 2);
-            double s = a0.x * r0.x + a0.y * r0.y + a1.x * r1.x + a1.y * r1.y;
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) zj[row] = s;
-        }
-    }
-    __syncthreads();
-    if (blockIdx.x == 0 && tid < nb) z[j0 + tid] = zj[tid];
-    // r_i -= L[i, j-block] z_j for this CTA's rows below the block
-    const int row_base = j0 + DB + blockIdx.x * FWD_ROWS;
-    const double2 z0 = *reinterpret_cast<const double2*>(zj + lane * 4);
-    const double2 z1 = *reinterpret_cast<const double2*>(zj + lane * 4 + 2);
-    constexpr int RPW = FWD_ROWS / (TRSV_THREADS / 32);  // rows per warp
-    for (int r4 = 0; r4 < RPW; r4 += 4) {
-        double s[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            int i = row_base + warp * RPW + r4 + u;
-            s[u] = 0.0;
-            if (i < n) {
-                const double* src = L + (int64_t)i * ld + j0 + lane * 4;
-                const double2 a0 = *reinterpret_cast<const double2*>(src);
-                const double2 a1 = *reinterpret_cast<const double2*>(src + 2);
-                s[u] = a0.x * z0.x + a0.y * z0.y + a1.x * z1.x + a1.y * z1.y;
-            }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-            for (int u = 0; u < 4; u++) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
-        if (lane < 4) {
-            int i = row_base + warp * RPW + r4 + lane;
-            double v = lane == 0 ? s[0] : (lane == 1 ? s[1] : (lane == 2 ? s[2] : s[3]));
-            if (i < n) work[i] -= v;
-        }
-    }
-}
 
 __global__ void __launch_bounds__(TRSV_THREADS)
     trsv_bwd_step_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int n, int j0,
@@ -740,12 +680,15 @@ __global__ void __launch_bounds__(TRSV_THREADS)
     const int nb = min(DB, n - j0);
     if (tid < DB) sj[tid] = tid < nb ? work[j0 + tid] : 0.0;
     __syncthreads();
-    // alpha_j = inv(L_jj)^T s_j : column sums, two row halves per column
+    // alpha_j = inv(L_jj)^T s_j : column sums, two row halves per column (the zero upper triangle of the stored
+    // inverse makes the full 64-row loop exact; fixed trip count so the loads pipeline)
     {
         const int c = tid & (DB - 1), hlf = tid >> 7;
         double s = 0.0;
-        const int rbeg = hlf * (DB / 2), rend = rbeg + DB / 2;
-        for (int r = max(rbeg, c); r < rend; r++) s += invd[r * DB + c] * sj[r];
+        const double* col = invd + (hlf * (DB / 2)) * DB + c;
+        const double* sv = sj + hlf * (DB / 2);
+#pragma unroll 16
+        for (int r = 0; r < DB / 2; r++) s += col[r * DB] * sv[r];
         if (hlf == 1) upper_half[c] = s;
         __syncthreads();
         if (hlf == 0) aj[c] = s + upper_half[c];
@@ -766,6 +709,51 @@ __global__ void __launch_bounds__(TRSV_THREADS)
         work[c] -= a0;
         work[c + 1] -= a1;
     }
+}
+
+// alpha = T^T z for lower-triangular T = L^-1: alpha[c] = sum_{r >= c} T[r][c] z[r].  One CTA per 32 columns,
+// 8 row lanes per column; T is streamed once (32 columns = 256 contiguous bytes per row), fixed-order reduction.
+constexpr int GT_COLS = 32;
+__global__ void __launch_bounds__(256)
+    gemv_t_kernel(const double* __restrict__ T, int64_t ld, int64_t sT, int n, const double* __restrict__ z, int64_t sZ,
+                  double* alpha, int64_t sAlpha) {
+    __shared__ double red[8][GT_COLS + 1];
+    const int64_t b = blockIdx.y;
+    T += b * sT;
+    z += b * sZ;
+    alpha += b * sAlpha;
+    const int c0 = blockIdx.x * GT_COLS;
+    const int cl = threadIdx.x & (GT_COLS - 1), rl = threadIdx.x >> 5;
+    const int c = c0 + cl;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (c < n) {
+        const double* col = T + c;
+        int r = c0 + rl;
+        for (; r + 24 < n; r += 32) {  // 4 independent loads in flight per thread
+            const double a0 = col[(int64_t)r * ld], a1 = col[(int64_t)(r + 8) * ld];
+            const double a2 = col[(int64_t)(r + 16) * ld], a3 = col[(int64_t)(r + 24) * ld];
+            s0 += (r >= c ? a0 : 0.0) * z[r];
+            s1 += (r + 8 >= c ? a1 : 0.0) * z[r + 8];
+            s2 += (r + 16 >= c ? a2 : 0.0) * z[r + 16];
+            s3 += (r + 24 >= c ? a3 : 0.0) * z[r + 24];
+        }
+        for (; r < n; r += 8)
+            if (r >= c) s0 += col[(int64_t)r * ld] * z[r];
+    }
+    red[rl][cl] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (rl == 0 && c < n) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += red[k][cl];
+        alpha[c] = s;
+    }
+}
+
+// dst[b][0..n) = src[b][0..n) with independent batch strides (y -> row n of the matrix, z -> work vector)
+__global__ void copy_rows_kernel(const double* src, int64_t sSrc, double* dst, int64_t sDst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[(int64_t)blockIdx.y * sDst + i] = src[(int64_t)blockIdx.y * sSrc + i];
 }
 
 __global__ void __launch_bounds__(256)
@@ -967,16 +955,6 @@ void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* i
     CUGP_CUDA(cudaGetLastError());
 }
 
-void launch_trsv_forward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd, double* work,
-                         double* z, int64_t sVec, int batch, cudaStream_t st) {
-    for (int j0 = 0; j0 < n; j0 += DB) {
-        int below = n - (j0 + DB);
-        int ctas = below > 0 ? cdiv(below, FWD_ROWS) : 1;
-        trsv_fwd_step_kernel<<<dim3(ctas, batch), TRSV_THREADS, 0, st>>>(L, ld, sL, n, j0, invd, sInvd, work, z, sVec);
-    }
-    CUGP_CUDA(cudaGetLastError());
-}
-
 void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd, double* work,
                           double* alpha, int64_t sVec, int batch, cudaStream_t st) {
     int last = (cdiv(n, DB) - 1) * DB;
@@ -984,6 +962,18 @@ void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const 
         int ctas = j0 > 0 ? cdiv(j0, BWD_COLS) : 1;
         trsv_bwd_step_kernel<<<dim3(ctas, batch), TRSV_THREADS, 0, st>>>(L, ld, sL, n, j0, invd, sInvd, work, alpha, sVec);
     }
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_gemv_t(const double* T, int64_t ld, int64_t sT, int n, const double* z, int64_t sZ, double* alpha,
+                   int64_t sAlpha, int batch, cudaStream_t st) {
+    gemv_t_kernel<<<dim3(cdiv(n, GT_COLS), batch), 256, 0, st>>>(T, ld, sT, n, z, sZ, alpha, sAlpha);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_copy_rows(const double* src, int64_t sSrc, double* dst, int64_t sDst, int n, int batch, cudaStream_t st) {
+    if (n <= 0 || batch <= 0) return;
+    copy_rows_kernel<<<dim3(cdiv(n, 256), batch), 256, 0, st>>>(src, sSrc, dst, sDst, n);
     CUGP_CUDA(cudaGetLastError());
 }
 

@@ -48,13 +48,16 @@ void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* i
 void debug_diag_phases(double* A, int64_t ld, int n, double* invd, double* logdet, long long* stamps_dev, cudaStream_t st);
 void set_diag_variant(int v);  // 1 (default): blocked DMMA kernel; 0: column-at-a-time kernel
 
-// ---- K3: blocked triangular solves L z = y, L^T alpha = z (matrixops.cpp:145-164) with the stored
-// inverses of the diagonal blocks; one launch per 128-column block and sweep.
-void launch_trsv_forward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd,
-                         double* work, double* z, int64_t sVec, int batch, cudaStream_t st);
+// ---- K3: alpha = L^-T z.  (The forward substitution is fused into the Cholesky, gp.cu.)
+// Blocked backward sweep L^T alpha = z (matrixops.cpp:156-164) with the stored inverses of the diagonal blocks;
+// one launch per 128-row block.  `work` holds z on entry and is consumed.
 void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd,
                           double* work, double* alpha, int64_t sVec, int batch, cudaStream_t st);
-// scal[batch][4] = (y'alpha, logdet, LL, 0) with LL = -0.5*(quad + logdet + n*1.83787) (covkernel.cpp:127)
+// alpha = T^T z with T = L^-1 lower triangular: one streaming pass (used whenever T exists)
+void launch_gemv_t(const double* T, int64_t ld, int64_t sT, int n, const double* z, int64_t sZ, double* alpha,
+                   int64_t sAlpha, int batch, cudaStream_t st);
+void launch_copy_rows(const double* src, int64_t sSrc, double* dst, int64_t sDst, int n, int batch, cudaStream_t st);
+// scal[batch][4] = (u'v, logdet, LL, 0) for vectors u, v (u = v = z: quad = z'z = y'K^-1 y) with LL = -0.5*(quad + logdet + n*1.83787) (covkernel.cpp:127)
 void launch_ll_finalize(const double* y, const double* alpha, int64_t sVec, int n, const double* logdet_part,
                         int nblk, double* scal, int batch, cudaStream_t st);
 

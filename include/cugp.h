@@ -102,12 +102,13 @@ int cugp_covsum_grad_resident(cugp_covsum *h, double grad[3]);
 int cugp_covsum_scalars_resident(cugp_covsum *h, double out3[3]);
 /* alpha = K^-1 y of the resident problem (n values) */
 int cugp_covsum_alpha_resident(cugp_covsum *h, double *alpha);
-/* Factorise only (covariance build + Cholesky); *seconds_chol = device time of the Cholesky alone
- * (CUDA events on the launching stream), for the FP64 roofline (n^3/3 flop). */
+/* Factorise only: covariance build, then the Cholesky with y appended as an extra row (which yields z = L^-1 y,
+ * y'K^-1 y = z'z, log det and LL without a forward sweep); *ms_chol = device time of that second part (CUDA events
+ * on the launching stream), for the FP64 roofline (n^3/3 flop). */
 int cugp_covsum_factorize_resident(cugp_covsum *h, float *ms_cov, float *ms_chol);
 
-/* Forward + backward solves, log-det and LL alone on the cached factor (factorises first if needed): device time
- * in ms, for the HBM roofline of the solves (2 * 4 n (n+1) bytes: L is streamed once per sweep). */
+/* alpha = L^-T z alone on the cached factor (factorises first if needed; the forward substitution z = L^-1 y is fused
+ * into the Cholesky): device time in ms, for the HBM roofline of the solve (4 n (n+1) bytes: L is streamed once). */
 int cugp_covsum_solve_resident(cugp_covsum *h, float *ms_solve);
 
 /* Dominant-kernel timing for the roofline: with profiling enabled every SYRK trailing-update launch of the
