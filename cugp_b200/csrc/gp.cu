@@ -256,7 +256,7 @@ GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(
 GpBatch::~GpBatch() {
     if (st) cudaStreamSynchronize(st);
     dfree(X); dfree(y); dfree(Kb); dfree(invd); dfree(logdet_part); dfree(work); dfree(z); dfree(alpha); dfree(scal);
-    dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout);
+    dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout); dfree(tpart);
     dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar);
     if (hstage) cudaFreeHost(hstage);
     for (cudaEvent_t e : prof.ev) cudaEventDestroy(e);
@@ -365,8 +365,9 @@ void GpBatch::solve() {
     } else {
         const int64_t sI = (int64_t)nblk * kDiag * kDiag;
         launch_copy_rows(zrow, mat_stride(), work, n, n, B, st);  // the sweep consumes its right-hand side
-        launch_trsv_backward(Kb, ld, mat_stride(), n, invd, sI, work, alpha, n, B, st);
-        launches += 1 + nblk;
+        dalloc(tpart, trsv_backward_scratch(n, B));
+        launch_trsv_backward(Kb, ld, mat_stride(), n, invd, sI, work, alpha, n, tpart, B, st);
+        launches += 1 + nblk + 2 * (cdiv(n, 1024) - 1);
     }
     have_alpha = true;
 }

@@ -32,6 +32,7 @@ struct GpBatch {
     double* scal = nullptr;                 // [B][4] quad, logdet, LL
     double *Tb = nullptr, *Wb = nullptr;    // [B][n][ld] lazily: T = L^-1 ; scratch, then Kinv (lower)
     double *gradpart = nullptr, *gradout = nullptr;
+    double* tpart = nullptr;                // partial sums of the backward sweep's panel launches (lazily)
     // prediction workspace (lazily sized)
     double *Xt = nullptr, *Ks = nullptr, *meanpart = nullptr, *css = nullptr, *pmean = nullptr, *pvar = nullptr;
     int pred_cap = 0;

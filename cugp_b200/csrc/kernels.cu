@@ -663,14 +663,17 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
 // it to its own slice of the remaining right-hand side, so the sweep streams L exactly once.
 // ------------------------------------------------------------------------------------------------
 constexpr int TRSV_THREADS = 256;
-constexpr int BWD_COLS = 512;   // columns of the block row handled per CTA
+constexpr int BWD_COLS = 512;   // columns per CTA of the panel kernel
+constexpr int BWD_STEP_COLS = 128;  // columns per CTA of the step kernel (4 row groups x 64 column pairs)
 
+// One 128-row block of the backward sweep.  The launch is latency bound (a chain of dependent global round
+// trips), so every load batch is issued in full before its first use: 32 independent loads per thread.
 __global__ void __launch_bounds__(TRSV_THREADS)
-    trsv_bwd_step_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int n, int j0,
+    trsv_bwd_step_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int n, int j0, int c_lo,
                          const double* __restrict__ invd, int64_t sInvd, double* work, double* alpha, int64_t sVec) {
     __shared__ double sj[DB];
     __shared__ double aj[DB];
-    __shared__ double upper_half[DB];
+    __shared__ double part[4][BWD_STEP_COLS];
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.y;
     L += b * sL;
@@ -679,36 +682,108 @@ __global__ void __launch_bounds__(TRSV_THREADS)
     alpha += b * sVec;
     const int nb = min(DB, n - j0);
     if (tid < DB) sj[tid] = tid < nb ? work[j0 + tid] : 0.0;
-    __syncthreads();
-    // alpha_j = inv(L_jj)^T s_j : column sums, two row halves per column (the zero upper triangle of the stored
-    // inverse makes the full 64-row loop exact; fixed trip count so the loads pipeline)
+    // alpha_j = inv(L_jj)^T s_j : thread (c, half) sums 64 rows of column c; the loads do not depend on s_j, so they
+    // are in flight while it arrives (the zero upper triangle of the stored inverse makes the full loop exact)
     {
         const int c = tid & (DB - 1), hlf = tid >> 7;
-        double s = 0.0;
         const double* col = invd + (hlf * (DB / 2)) * DB + c;
-        const double* sv = sj + hlf * (DB / 2);
-#pragma unroll 16
-        for (int r = 0; r < DB / 2; r++) s += col[r * DB] * sv[r];
-        if (hlf == 1) upper_half[c] = s;
-        __syncthreads();
-        if (hlf == 0) aj[c] = s + upper_half[c];
+        double s = 0.0;
+#pragma unroll
+        for (int r0 = 0; r0 < DB / 2; r0 += 32) {
+            double v[32];
+#pragma unroll
+            for (int u = 0; u < 32; u++) v[u] = col[(r0 + u) * DB];
+            if (r0 == 0) __syncthreads();  // s_j is in shared memory
+#pragma unroll
+            for (int u = 0; u < 32; u++) s += v[u] * sj[hlf * (DB / 2) + r0 + u];
+        }
+        part[hlf][c] = s;
     }
     __syncthreads();
+    if (tid < DB) aj[tid] = part[0][tid] + part[1][tid];
+    __syncthreads();
     if (blockIdx.x == 0 && tid < nb) alpha[j0 + tid] = aj[tid];
-    // s[c] -= sum_r L[j0+r][c] alpha_j[r] for this CTA's columns left of the block
-    const int c = blockIdx.x * BWD_COLS + tid * 2;
+    // s[c] -= sum_r L[j0+r][c] alpha_j[r] for this CTA's columns in [c_lo, j0) (c_lo: start of the outer panel):
+    // thread (column pair, row group) covers 32 rows of 2 columns
+    const int cp = tid & 63, rg = tid >> 6;
+    const int c = c_lo + blockIdx.x * BWD_STEP_COLS + cp * 2;
+    double a0 = 0.0, a1 = 0.0;
     if (c < j0) {
-        double a0 = 0.0, a1 = 0.0;
-        const double* src = L + (int64_t)j0 * ld + c;
-#pragma unroll 8
-        for (int r = 0; r < nb; r++) {
-            const double2 v = *reinterpret_cast<const double2*>(src + (int64_t)r * ld);
-            a0 += v.x * aj[r];
-            a1 += v.y * aj[r];
+        const double* src = L + (int64_t)(j0 + rg * 32) * ld + c;
+        double2 v[32];
+#pragma unroll
+        for (int u = 0; u < 32; u++)
+            v[u] = (rg * 32 + u < nb) ? *reinterpret_cast<const double2*>(src + (int64_t)u * ld) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < 32; u++) {
+            a0 += v[u].x * aj[rg * 32 + u];
+            a1 += v[u].y * aj[rg * 32 + u];
         }
-        work[c] -= a0;
-        work[c + 1] -= a1;
     }
+    __syncthreads();  // part[] is reused
+    part[rg][cp * 2] = a0;
+    part[rg][cp * 2 + 1] = a1;
+    __syncthreads();
+    if (tid < BWD_STEP_COLS) {
+        const int cc = c_lo + blockIdx.x * BWD_STEP_COLS + tid;
+        if (cc < j0) work[cc] -= (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+    }
+}
+
+// Outer step of the two-level backward sweep: all columns left of a finished panel of rows [P0, P0 + rows) receive
+// s[c] -= sum_r L[P0+r][c] alpha[P0+r].  The rows x P0 slab of L is streamed once at full width by a 2-D grid
+// (128 columns x 128 rows per CTA, 32 independent 16-byte loads per thread); the row chunks leave partial sums
+// that a second small kernel adds in a fixed order (deterministic, no atomics).  The per-128-row launches
+// inside the panel only touch the panel's own columns and stay in L2.
+constexpr int BWD_PANEL = 1024;
+constexpr int BWD_PCOLS = 128, BWD_PROWS = 128, BWD_PCHUNKS = BWD_PANEL / BWD_PROWS;
+__global__ void __launch_bounds__(TRSV_THREADS)
+    trsv_bwd_panel_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int P0, int rows,
+                          const double* __restrict__ alpha, int64_t sVec, double* partial, int64_t sPart, int n) {
+    __shared__ double ap[BWD_PROWS];
+    __shared__ double red[4][BWD_PCOLS];
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.z;
+    L += b * sL;
+    alpha += b * sVec;
+    partial += b * sPart + (int64_t)blockIdx.y * n;
+    const int r0 = blockIdx.y * BWD_PROWS;                 // first row of this chunk inside the panel
+    if (tid < BWD_PROWS) ap[tid] = (r0 + tid < rows) ? alpha[P0 + r0 + tid] : 0.0;
+    const int cp = tid & 63, rg = tid >> 6;                // column pair, row group (32 rows each)
+    const int c = blockIdx.x * BWD_PCOLS + cp * 2;
+    double a0 = 0.0, a1 = 0.0;
+    double2 v[32];
+    if (c < P0) {
+        const double* src = L + (int64_t)(P0 + r0 + rg * 32) * ld + c;
+#pragma unroll
+        for (int u = 0; u < 32; u++)
+            v[u] = (r0 + rg * 32 + u < rows) ? *reinterpret_cast<const double2*>(src + (int64_t)u * ld) : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    if (c < P0) {
+#pragma unroll
+        for (int u = 0; u < 32; u++) {
+            a0 += v[u].x * ap[rg * 32 + u];
+            a1 += v[u].y * ap[rg * 32 + u];
+        }
+    }
+    red[rg][cp * 2] = a0;
+    red[rg][cp * 2 + 1] = a1;
+    __syncthreads();
+    if (tid < BWD_PCOLS) {
+        const int cc = blockIdx.x * BWD_PCOLS + tid;
+        if (cc < P0) partial[cc] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+    }
+}
+
+__global__ void trsv_bwd_panel_reduce_kernel(const double* partial, int64_t sPart, int n, int chunks, int P0, double* work,
+                                             int64_t sVec) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P0) return;
+    const double* p = partial + (int64_t)blockIdx.y * sPart + c;
+    double s = 0.0;
+    for (int k = 0; k < chunks; k++) s += p[(int64_t)k * n];
+    work[(int64_t)blockIdx.y * sVec + c] -= s;
 }
 
 // alpha = T^T z for lower-triangular T = L^-1: alpha[c] = sum_{r >= c} T[r][c] z[r].  One CTA per 32 columns,
@@ -955,12 +1030,26 @@ void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* i
     CUGP_CUDA(cudaGetLastError());
 }
 
+size_t trsv_backward_scratch(int n, int batch) { return (size_t)BWD_PCHUNKS * n * batch; }
+
 void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd, double* work,
-                          double* alpha, int64_t sVec, int batch, cudaStream_t st) {
-    int last = (cdiv(n, DB) - 1) * DB;
-    for (int j0 = last; j0 >= 0; j0 -= DB) {
-        int ctas = j0 > 0 ? cdiv(j0, BWD_COLS) : 1;
-        trsv_bwd_step_kernel<<<dim3(ctas, batch), TRSV_THREADS, 0, st>>>(L, ld, sL, n, j0, invd, sInvd, work, alpha, sVec);
+                          double* alpha, int64_t sVec, double* scratch, int batch, cudaStream_t st) {
+    for (int P1 = n; P1 > 0;) {
+        const int P0 = ((P1 - 1) / BWD_PANEL) * BWD_PANEL;
+        const int last = P0 + ((P1 - P0 - 1) / DB) * DB;
+        for (int j0 = last; j0 >= P0; j0 -= DB) {
+            const int ctas = j0 > P0 ? cdiv(j0 - P0, BWD_STEP_COLS) : 1;
+            trsv_bwd_step_kernel<<<dim3(ctas, batch), TRSV_THREADS, 0, st>>>(L, ld, sL, n, j0, P0, invd, sInvd, work, alpha,
+                                                                            sVec);
+        }
+        if (P0 > 0) {
+            const int chunks = cdiv(P1 - P0, BWD_PROWS);
+            trsv_bwd_panel_kernel<<<dim3(cdiv(P0, BWD_PCOLS), chunks, batch), TRSV_THREADS, 0, st>>>(
+                L, ld, sL, P0, P1 - P0, alpha, sVec, scratch, (int64_t)BWD_PCHUNKS * n, n);
+            trsv_bwd_panel_reduce_kernel<<<dim3(cdiv(P0, 256), batch), 256, 0, st>>>(scratch, (int64_t)BWD_PCHUNKS * n, n, chunks,
+                                                                                    P0, work, sVec);
+        }
+        P1 = P0;
     }
     CUGP_CUDA(cudaGetLastError());
 }

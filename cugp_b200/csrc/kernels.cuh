@@ -50,9 +50,11 @@ void set_diag_variant(int v);  // 1 (default): blocked DMMA kernel; 0: column-at
 
 // ---- K3: alpha = L^-T z.  (The forward substitution is fused into the Cholesky, gp.cu.)
 // Blocked backward sweep L^T alpha = z (matrixops.cpp:156-164) with the stored inverses of the diagonal blocks;
-// one launch per 128-row block.  `work` holds z on entry and is consumed.
+// two-level: 128-row block steps inside 1024-row panels, one full-width streaming launch per panel.  `work` holds z
+// on entry and is consumed.
 void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd,
-                          double* work, double* alpha, int64_t sVec, int batch, cudaStream_t st);
+                          double* work, double* alpha, int64_t sVec, double* scratch, int batch, cudaStream_t st);
+size_t trsv_backward_scratch(int n, int batch);  // doubles needed in `scratch`
 // alpha = T^T z with T = L^-1 lower triangular: one streaming pass (used whenever T exists)
 void launch_gemv_t(const double* T, int64_t ld, int64_t sT, int n, const double* z, int64_t sZ, double* alpha,
                    int64_t sAlpha, int batch, cudaStream_t st);

@@ -2,6 +2,7 @@
 // linking this file proves the header shim and libcugp.so cover the reference's call surface
 // (cpp_serial_gp/covkernel.h:3-38, common/matrixops.h:5-25, distributed_gp/BCM.h:2-27).  With a GPU it also runs:
 //   shim_probe            -> prints LL, gradient, predictions of a small problem (checked by tests/test_shim.py)
+//   shim_probe <inputs> <labels> <numtrain> <numtest>  -> the GPU-flavour free functions (cugp_shim/cuda_gp.h)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -10,6 +11,7 @@
 #include "cugp_shim/matrixops.h"
 #include "cugp_shim/covkernel.h"
 #include "cugp_shim/BCM.h"
+#include "cugp_shim/cuda_gp.h"
 
 static double** alloc2(int r, int c) {
     double** M = new double*[r];
@@ -18,6 +20,21 @@ static double** alloc2(int r, int c) {
 }
 
 int main(int argc, char** argv) {
+    if (argc == 5) {  // GPU-flavour facade: shim_probe <inputs> <labels> <numtrain> <numtest>
+        const int ntr = std::atoi(argv[3]), nte = std::atoi(argv[4]);
+        setup(ntr, argv[1], argv[2]);
+        double g[3];
+        std::printf("FLL %.17g\n", compute_log_likelihood());
+        compute_gradient_log_hyperparams(g);
+        std::printf("FGRAD %.17g %.17g %.17g\n", g[0], g[1], g[2]);
+        Eigen::VectorXd v(3);
+        v[0] = 1.5; v[1] = 1.5; v[2] = 1.5;
+        set_loghyper_eigen(v);
+        std::printf("FLL2 %.17g FTH %.17g\n", compute_log_likelihood(), get_loghyperparam()[0]);
+        testing_phase(ntr, nte);
+        std::printf("FNLPP %.17g\n", cugp_shim::gpu_state().nlpp);
+        return 0;
+    }
     const int n = 96, d = 2, m = 8;
     double** X = alloc2(n + m, d);
     double* y = new double[n + m];

@@ -91,9 +91,9 @@ def test_reference_drivers_build_unchanged_against_shim():
     assert os.path.exists(os.path.join(OUT, "serial_gp")) and os.path.exists(os.path.join(OUT, "distributed_ver1"))
 
 
-def _run(exe, cwd=None, timeout=600):
+def _run(exe, cwd=None, timeout=600, args=()):
     env = dict(os.environ, LD_LIBRARY_PATH=LIBDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-    r = subprocess.run([exe], capture_output=True, text=True, cwd=cwd, env=env, timeout=timeout)
+    r = subprocess.run([exe, *args], capture_output=True, text=True, cwd=cwd, env=env, timeout=timeout)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     return r.stdout
 
@@ -159,3 +159,37 @@ def test_reference_bcm_driver_runs_on_the_shim():
     got = [float(v) for v in finals[-1]]
     th, _, _ = oracle.port().cg_solve(d["X"], d["y"], [1.5, 1.5, 1.5], K=4)
     assert [f"{v:.6f}" for v in got] == [f"{v:.6f}" for v in th], (got, th)
+
+
+@pytest.mark.gpu
+def test_gpu_flavour_facade_reproduces_reference_logs():
+    """cugp_shim/cuda_gp.h: setup / compute_log_likelihood / compute_gradient_log_hyperparams / set_loghyper_eigen /
+    testing_phase (cuda_src/main.cpp:16-36).  setup() starts at theta = 0.5: the 128 x 2 set must give the LL of the
+    reference's own log cuda_ref/seeee:19 (-203.386580), and at theta = 1.5 that of
+    cuda_bettersinglenode_ver2/REF:33 (-319.512020), to the printed digits."""
+    from tests.conftest import load_data, load_golden
+    import cugp_b200 as cg
+    exe = os.path.join(OUT, "shim_probe")
+    if not os.path.exists(exe):
+        exe = _build_probe()
+    d = load_data("si128x2")
+    gold = load_golden()
+    with tempfile.TemporaryDirectory() as t:
+        fi, fl = os.path.join(t, "in.txt"), os.path.join(t, "lab.txt")
+        with open(fi, "w") as f:
+            f.write("64 2\n")                               # the header lies about the row count (SURVEY Q11)
+            for row in d["X"]:
+                f.write(" ".join(repr(float(v)) for v in row) + " \n")
+        with open(fl, "w") as f:
+            for v in d["y"]:
+                f.write(repr(float(v)) + "\n")
+        out = _run(exe, args=[fi, fl, "128", "0"])
+        out96 = _run(exe, args=[fi, fl, "96", "32"])
+    val = {l.split()[0]: [float(x) for x in l.split()[1:] if x[0] in "-0123456789n"] for l in out.splitlines() if l.startswith("F")}
+    assert f"{val['FLL'][0]:.6f}" == f"{gold['seeee_log']['ll']:.6f}"
+    assert f"{val['FLL2'][0]:.6f}" == f"{gold['REF_log']['ll_sequence'][0]:.6f}"
+    v96 = {l.split()[0]: [float(x) for x in l.split()[1:] if x[0] in "-0123456789n"] for l in out96.splitlines() if l.startswith("F")}
+    g = cg.Covsum(96, 2)
+    g.set_loghyperparam([1.5, 1.5, 1.5])
+    mu, var = g.compute_test_means_and_variances(d["X"][:96], d["y"][:96], d["X"][96:])
+    assert abs(v96["FNLPP"][0] - g.get_negative_log_predprob(d["y"][96:], mu, var)) <= 1e-12
