@@ -142,14 +142,6 @@ int cugp_set_tuning(const char* key, long value) {
         set_lookahead(value != 0);
         return CUGP_OK;
     }
-    if (std::strcmp(key, "gemm_kernel") == 0) {
-        set_gemm_variant(value != 0);
-        return CUGP_OK;
-    }
-    if (std::strcmp(key, "diag_kernel") == 0) {
-        set_diag_variant(value != 0);
-        return CUGP_OK;
-    }
     set_last_error("unknown tuning key '%s'", key);
     return CUGP_ERR_INVALID;
 }

@@ -1,14 +1,10 @@
-// gemm_dmma.cu -- see gemm_dmma.cuh.  Hand-written sm_100a kernel: cp.async multi-stage pipeline +
+// gemm_dmma.cu -- see gemm_dmma.cuh.  Hand-written sm_100a kernel: warp-specialised cp.async/mbarrier pipeline +
 // mma.sync.m8n8k4.f64 (DMMA.8x8x4).  No cuBLAS anywhere in the product path.
 #include "gemm_dmma.cuh"
 
 namespace cugp {
 
 namespace {
-
-constexpr int BK = 16;      // k-depth of one pipeline stage (4 DMMA k-steps)
-constexpr int STAGES = 4;
-constexpr int PAD = 4;      // doubles; (stride mod 16) == 4 keeps 8-byte fragment loads conflict-free
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -25,255 +21,14 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
-// Stage one operand tile.  KC: tile stored [ROWS][BK+PAD] from a [rows][K] matrix.
-//                          RC: tile stored [BK][ROWS+PAD] from a [K][rows] matrix.
-template <int ROWS, bool KC, int NT>
-__device__ __forceinline__ void load_tile(double* smem, const double* __restrict__ g, int64_t ld, int row0,
-                                          int rows_total, int k0, int k_hi, int tid) {
-    if (KC) {
-        constexpr int CH = BK / 2;  // 16-byte chunks per row
-#pragma unroll
-        for (int c = tid; c < ROWS * CH; c += NT) {
-            int r = c / CH, kc = (c % CH) * 2;
-            int grow = row0 + r, gk = k0 + kc;
-            int bytes = 0;
-            if (grow < rows_total) bytes = min(max((k_hi - gk) * 8, 0), 16);
-            const double* src = bytes ? g + (int64_t)grow * ld + gk : g;
-            cp_async16(smem + r * (BK + PAD) + kc, src, bytes);
-        }
-    } else {
-        constexpr int CH = ROWS / 2;
-#pragma unroll
-        for (int c = tid; c < BK * CH; c += NT) {
-            int kr = c / CH, mc = (c % CH) * 2;
-            int gk = k0 + kr, grow = row0 + mc;
-            int bytes = 0;
-            if (gk < k_hi) bytes = min(max((rows_total - grow) * 8, 0), 16);
-            const double* src = bytes ? g + (int64_t)gk * ld + grow : g;
-            cp_async16(smem + kr * (ROWS + PAD) + mc, src, bytes);
-        }
-    }
-}
-
-template <int ROWS, bool KC>
-__host__ __device__ constexpr int tile_doubles() {
-    return KC ? ROWS * (BK + PAD) : BK * (ROWS + PAD);
-}
-
-template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) dgemm_dmma_kernel(const GemmParams p) {
-    constexpr int NT = WARPS_M * WARPS_N * 32;
-    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
-    constexpr int MI = WM / 8, NI = WN / 8;
-    constexpr int A_SZ = tile_doubles<BM, A_KC>();
-    constexpr int B_SZ = tile_doubles<BN, B_KC>();
-    extern __shared__ __align__(16) double smem[];
-    double* As = smem;
-    double* Bs = smem + STAGES * A_SZ;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, q = lane & 3;
-    const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
-
-    int ti, tj;
-    if (p.lower_tiles) {
-        // linear index over the tiles with ti >= tj of an M x N (M >= N) lower trapezoid: first the
-        // triangle of the top N x N square row by row, then the full-width tile rows below it
-        const int tn = (p.N + BN - 1) / BN;
-        const int tri = tn * (tn + 1) / 2;
-        int x = blockIdx.x;
-        if (x < tri) {
-            ti = (int)((sqrt(8.0 * (double)x + 1.0) - 1.0) * 0.5);
-            while ((int64_t)(ti + 1) * (ti + 2) / 2 <= x) ti++;
-            while ((int64_t)ti * (ti + 1) / 2 > x) ti--;
-            tj = x - (int)((int64_t)ti * (ti + 1) / 2);
-        } else {
-            x -= tri;
-            ti = tn + x / tn;
-            tj = x % tn;
-        }
-    } else {
-        int tiles_n = (p.N + BN - 1) / BN;
-        ti = blockIdx.x / tiles_n;
-        tj = blockIdx.x % tiles_n;
-    }
-    const int m0 = ti * BM, n0 = tj * BN;
-    const int64_t b = blockIdx.y;
-    int64_t offA, offB, offC;
-    if (p.batch_inner > 1) {
-        const int64_t bi = b % p.batch_inner, bo = b / p.batch_inner;
-        offA = bi * p.sA + bo * p.sA2;
-        offB = bi * p.sB + bo * p.sB2;
-        offC = bi * p.sC + bo * p.sC2;
-    } else {
-        offA = b * p.sA;
-        offB = b * p.sB;
-        offC = b * p.sC;
-    }
-    const double* __restrict__ A = p.A + offA;
-    const double* __restrict__ B = p.B + offB;
-
-    int k_lo = 0, k_hi = p.K;
-    if (p.klo_ti) k_lo = max(k_lo, m0);
-    if (p.klo_tj) k_lo = max(k_lo, n0);
-    if (p.khi_ti) k_hi = min(k_hi, m0 + BM);
-    if (p.khi_tj) k_hi = min(k_hi, n0 + BN);
-    const int nk = k_hi > k_lo ? (k_hi - k_lo + BK - 1) / BK : 0;
-
-    double acc[MI][NI][2];
-#pragma unroll
-    for (int i = 0; i < MI; i++)
-#pragma unroll
-        for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    // prologue
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nk) {
-            load_tile<BM, A_KC, NT>(As + s * A_SZ, A, p.lda, m0, p.M, k_lo + s * BK, k_hi, tid);
-            load_tile<BN, B_KC, NT>(Bs + s * B_SZ, B, p.ldb, n0, p.N, k_lo + s * BK, k_hi, tid);
-        }
-        cp_async_commit();
-    }
-
-    for (int kt = 0; kt < nk; kt++) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            int nxt = kt + STAGES - 1;
-            if (nxt < nk) {
-                int s = nxt % STAGES;
-                load_tile<BM, A_KC, NT>(As + s * A_SZ, A, p.lda, m0, p.M, k_lo + nxt * BK, k_hi, tid);
-                load_tile<BN, B_KC, NT>(Bs + s * B_SZ, B, p.ldb, n0, p.N, k_lo + nxt * BK, k_hi, tid);
-            }
-            cp_async_commit();
-        }
-        const double* as = As + (kt % STAGES) * A_SZ;
-        const double* bs = Bs + (kt % STAGES) * B_SZ;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            double af[MI], bf[NI];
-#pragma unroll
-            for (int i = 0; i < MI; i++)
-                af[i] = A_KC ? as[(wm0 + i * 8 + g) * (BK + PAD) + kk + q] : as[(kk + q) * (BM + PAD) + wm0 + i * 8 + g];
-#pragma unroll
-            for (int j = 0; j < NI; j++)
-                bf[j] = B_KC ? bs[(wn0 + j * 8 + g) * (BK + PAD) + kk + q] : bs[(kk + q) * (BN + PAD) + wn0 + j * 8 + g];
-#pragma unroll
-            for (int i = 0; i < MI; i++)
-#pragma unroll
-                for (int j = 0; j < NI; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-    }
-    cp_async_wait<0>();
-
-    if (p.colsumsq) {
-        // Epilogue for the predictive variance: sum over this tile's rows of (alpha*acc)^2, per column.
-        __syncthreads();
-        double* red = smem;  // [WARPS_M][BN]
-#pragma unroll
-        for (int j = 0; j < NI; j++) {
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int i = 0; i < MI; i++) {
-                int row = m0 + wm0 + i * 8 + g;
-                if (row < p.M) {
-                    double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-                    s0 += v0 * v0;
-                    s1 += v1 * v1;
-                }
-            }
-#pragma unroll
-            for (int off = 4; off < 32; off <<= 1) {
-                s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-            }
-            if (g == 0) {
-                red[(warp / WARPS_N) * BN + wn0 + j * 8 + 2 * q] = s0;
-                red[(warp / WARPS_N) * BN + wn0 + j * 8 + 2 * q + 1] = s1;
-            }
-        }
-        __syncthreads();
-        double* out = p.colsumsq + b * p.sCss + (int64_t)ti * p.N;
-        for (int c = tid; c < BN; c += NT) {
-            if (n0 + c < p.N) {
-                double s = 0.0;
-#pragma unroll
-                for (int w = 0; w < WARPS_M; w++) s += red[w * BN + c];
-                out[n0 + c] = s;
-            }
-        }
-        return;
-    }
-
-    double* __restrict__ C = p.C + offC;
-    const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    const bool interior = vec_ok && (m0 + BM <= p.M) && (n0 + BN <= p.N);
-    if (interior) {
-        // All loads of a batch are issued before the first use: one L2 round trip per batch instead of one per
-        // element pair (a load placed after a store to the same array cannot be hoisted by the compiler).
-        constexpr int IB = MI >= 4 ? 4 : MI;
-        double* base = C + (int64_t)(m0 + wm0 + g) * p.ldc + n0 + wn0 + 2 * q;
-#pragma unroll
-        for (int i0 = 0; i0 < MI; i0 += IB) {
-            double2 old[IB][NI];
-            if (p.beta != 0.0) {
-#pragma unroll
-                for (int i = 0; i < IB; i++)
-#pragma unroll
-                    for (int j = 0; j < NI; j++)
-                        old[i][j] = *reinterpret_cast<const double2*>(base + (int64_t)(i0 + i) * 8 * p.ldc + j * 8);
-            }
-#pragma unroll
-            for (int i = 0; i < IB; i++)
-#pragma unroll
-                for (int j = 0; j < NI; j++) {
-                    double v0 = p.alpha * acc[i0 + i][j][0], v1 = p.alpha * acc[i0 + i][j][1];
-                    if (p.beta != 0.0) {
-                        v0 += p.beta * old[i][j].x;
-                        v1 += p.beta * old[i][j].y;
-                    }
-                    *reinterpret_cast<double2*>(base + (int64_t)(i0 + i) * 8 * p.ldc + j * 8) = make_double2(v0, v1);
-                }
-        }
-        return;
-    }
-#pragma unroll
-    for (int i = 0; i < MI; i++) {
-        int row = m0 + wm0 + i * 8 + g;
-        if (row >= p.M) continue;
-#pragma unroll
-        for (int j = 0; j < NI; j++) {
-            int col = n0 + wn0 + j * 8 + 2 * q;
-            if (col >= p.N) continue;
-            double* cp = C + (int64_t)row * p.ldc + col;
-            double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-            if (col + 1 < p.N && vec_ok) {
-                if (p.beta != 0.0) {
-                    double2 old = *reinterpret_cast<const double2*>(cp);
-                    v0 += p.beta * old.x;
-                    v1 += p.beta * old.y;
-                }
-                *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
-            } else {
-                if (p.beta != 0.0) v0 += p.beta * cp[0];
-                cp[0] = v0;
-                if (col + 1 < p.N) {
-                    if (p.beta != 0.0) v1 += p.beta * cp[1];
-                    cp[1] = v1;
-                }
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Warp-specialised variant (the default): a producer warp streams the operand tiles with zero-filling
+// Warp-specialised kernel: a producer warp group streams the operand tiles with zero-filling
 // 16-byte cp.async (LDGSTS) whose completion is tracked by per-stage mbarriers
 // (cp.async.mbarrier.arrive.noinc); the consumer warps only wait on a barrier, load fragments and issue
 // DMMA -- no CTA-wide __syncthreads and no address arithmetic in the math warps.  (Measured: feeding the
 // stages with one 1-D cp.async.bulk per 256-byte row instead capped the kernel at 19 TFLOP/s -- the copy
-// engine sustains only about one such request per 60 clocks per SM.)  BK = 32 halves the per-stage fixed costs of the cp.async kernel above.
+// engine sustains only about one such request per 60 clocks per SM; a classic all-warps cp.async kernel with
+// __syncthreads per 16-deep stage reached 26.5 TFLOP/s, this one 34.)
 // Tiles are rasterised in strips of 8 tile columns so the 148 resident CTAs share a few operand
 // panels (L2 hits instead of HBM re-reads when the panels exceed the 126 MB L2).
 // ------------------------------------------------------------------------------------------------
@@ -290,9 +45,6 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -307,12 +59,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
     } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 
 // Linear block index -> output tile.  lower: tiles with ti >= tj of a tm x tn (tm >= tn) trapezoid.
@@ -606,8 +352,6 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
     }
 }
 
-static int g_gemm_variant = 1;  // 1: warp-specialised bulk-copy kernel, 0: cp.async kernel
-
 template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC>
 void launch_ws(const GemmParams& p, cudaStream_t stream) {
     constexpr int NT = (WARPS_M * WARPS_N + NPW) * 32;
@@ -632,46 +376,15 @@ void launch_ws(const GemmParams& p, cudaStream_t stream) {
     CUGP_CUDA(cudaGetLastError());
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KC, bool B_KC>
-void launch_one(const GemmParams& p, cudaStream_t stream) {
-    constexpr int NT = WARPS_M * WARPS_N * 32;
-    constexpr size_t smem = (size_t)STAGES * (tile_doubles<BM, A_KC>() + tile_doubles<BN, B_KC>()) * sizeof(double);
-    static bool configured = false;
-    auto kern = dgemm_dmma_kernel<BM, BN, WARPS_M, WARPS_N, A_KC, B_KC>;
-    if (!configured) {
-        CUGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    int tiles_m = cdiv(p.M, BM), tiles_n = cdiv(p.N, BN);
-    int64_t tiles = (int64_t)tiles_m * tiles_n;
-    if (p.lower_tiles) {  // trapezoid: needs M >= N and square tiles
-        if (BM != BN || tiles_m < tiles_n) throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};
-        tiles = (int64_t)tiles_n * (tiles_n + 1) / 2 + (int64_t)(tiles_m - tiles_n) * tiles_n;
-    }
-    if (tiles <= 0 || p.batch <= 0) return;
-    dim3 grid((unsigned)tiles, (unsigned)p.batch);
-    kern<<<grid, NT, smem, stream>>>(p);
-    CUGP_CUDA(cudaGetLastError());
-}
-
 template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE>
 void launch_layout(const GemmParams& p, bool a_kc, bool b_kc, cudaStream_t stream) {
-    if (g_gemm_variant == 1) {
-        if (a_kc && b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, true, true>(p, stream);
-        else if (a_kc && !b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, true, false>(p, stream);
-        else if (!a_kc && !b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, false, false>(p, stream);
-        else launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, false, true>(p, stream);
-        return;
-    }
-    if (a_kc && b_kc) launch_one<BM, BN, WARPS_M, WARPS_N, true, true>(p, stream);
-    else if (a_kc && !b_kc) launch_one<BM, BN, WARPS_M, WARPS_N, true, false>(p, stream);
-    else if (!a_kc && !b_kc) launch_one<BM, BN, WARPS_M, WARPS_N, false, false>(p, stream);
-    else launch_one<BM, BN, WARPS_M, WARPS_N, false, true>(p, stream);
+    if (a_kc && b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, true, true>(p, stream);
+    else if (a_kc && !b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, true, false>(p, stream);
+    else if (!a_kc && !b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, false, false>(p, stream);
+    else launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, false, true>(p, stream);
 }
 
 }  // namespace
-
-void set_gemm_variant(int v) { g_gemm_variant = v; }
 
 int gemm_tile_m(GemmConfig cfg) { return cfg == GEMM_BIG ? 128 : 64; }
 

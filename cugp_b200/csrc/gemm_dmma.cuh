@@ -8,8 +8,8 @@
 //   TRTRI recursion        tmp  = L21 T11 ; T21 = -T22 tmp   (B row-contig; triangular k-ranges)
 //   LAUUM                  Kinv = T^T T              (A and B row-contig, k >= max(i,j))
 //   predictive variance    V    = T Kstar^T          (epilogue reduces column sums of squares)
-// Operands are staged global->shared with a 4-stage cp.async pipeline; shared rows are padded by 4
-// doubles so the 8-byte fragment loads of a half-warp fall in distinct 32-byte bank groups.
+// Operands are staged global->shared by a producer warp group (cp.async + mbarrier, 3-4 stages of k-depth 32);
+// shared rows are padded by 4 doubles so the 8-byte fragment loads of a half-warp fall in distinct bank pairs.
 #pragma once
 #include "common.cuh"
 
@@ -40,6 +40,5 @@ void launch_gemm(const GemmParams& p, bool a_kc, bool b_kc, GemmConfig cfg, cuda
 // Picks BIG when the grid fills the chip, SMALL otherwise.
 GemmConfig pick_config(int M, int N, int batch, bool lower_tiles);
 int gemm_tile_m(GemmConfig cfg);
-void set_gemm_variant(int v);  // 1 (default): warp-specialised bulk-copy kernel; 0: cp.async kernel
 
 }  // namespace cugp

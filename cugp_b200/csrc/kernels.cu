@@ -314,86 +314,20 @@ void launch_cov(const CovArgs& a, int64_t tiles, int batch, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2a: Cholesky + triangular inverse of a 128x128 diagonal block in shared memory.
+// K2a: Cholesky + triangular inverse of a 128x128 diagonal block in shared memory (one CTA per matrix).
 // S is 128 x 129: the lower triangle holds A -> L; the inverse is built in the strictly upper part,
-// R(i,j) = S[j][i+1] for i >= j, so one 132 KB array serves both (odd row stride: column walks are
+// T(i,j) = S[j][i+1] for i >= j, so one 132 KB array serves both (odd row stride: column walks are
 // conflict-free).
 // ------------------------------------------------------------------------------------------------
 constexpr int DB = kDiag;
 constexpr int DLD = DB + 1;
 constexpr int DIAG_THREADS = 512;
 
-__global__ void __launch_bounds__(DIAG_THREADS, 1)
-    potrf_diag_kernel(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd,
-                      double* logdet_part, int nblk, int blk) {
-    extern __shared__ __align__(16) double S[];
-    __shared__ double red[DB];
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;  // 32 x 16
-    const int64_t b = blockIdx.x;
-    double* Ab = A + b * sA + (int64_t)j0 * ld + j0;
-    const int nb = min(DB, n - j0);
-
-    for (int e = tid; e < DB * DLD; e += DIAG_THREADS) {
-        int i = e / DLD, j = e % DLD;
-        double v = 0.0;
-        if (j <= i) {  // lower triangle of A, identity padded
-            if (i < nb) v = Ab[(int64_t)i * ld + j];
-            else if (i == j) v = 1.0;
-        } else if (j == i + 1) {
-            v = 1.0;  // R = I
-        }
-        S[e] = v;
-    }
-    __syncthreads();
-
-    // Right-looking Cholesky, one column per step (matrixops.cpp:74-98 restricted to the block).
-    for (int k = 0; k < DB; k++) {
-        const double dk = sqrt(S[k * DLD + k]);  // negative pivot -> NaN, propagates (matrixops.cpp:77)
-        for (int i = k + 1 + tid; i < DB; i += DIAG_THREADS) S[i * DLD + k] = S[i * DLD + k] / dk;
-        __syncthreads();
-        if (tid == 0) S[k * DLD + k] = dk;
-        for (int i = k + 1 + ty; i < DB; i += 16) {
-            const double lik = S[i * DLD + k];
-            for (int j = k + 1 + tx; j <= i; j += 32) S[i * DLD + j] -= lik * S[j * DLD + k];
-        }
-        __syncthreads();
-    }
-
-    // Inverse by forward substitution against I, all columns at once (matrixops.cpp:330-340).
-    for (int k = 0; k < DB; k++) {
-        const double dk = S[k * DLD + k];
-        for (int j = tid; j <= k; j += DIAG_THREADS) S[j * DLD + k + 1] = S[j * DLD + k + 1] / dk;  // T[k][j]
-        __syncthreads();
-        for (int j = ty; j <= k; j += 16) {
-            const double tkj = S[j * DLD + k + 1];
-            for (int i = k + 1 + tx; i < DB; i += 32) S[j * DLD + i + 1] -= S[i * DLD + k] * tkj;
-        }
-        __syncthreads();
-    }
-
-    // write back: L11 with zeroed upper triangle, inv(L11) dense 128x128 (zero upper)
-    double* inv = invd + b * sInvd;
-    for (int e = tid; e < DB * DB; e += DIAG_THREADS) {
-        int i = e / DB, j = e % DB;
-        if (i < nb && j < nb) Ab[(int64_t)i * ld + j] = (j <= i) ? S[i * DLD + j] : 0.0;
-        inv[e] = (j <= i) ? S[j * DLD + i + 1] : 0.0;
-    }
-    if (tid < DB) red[tid] = log(S[tid * DLD + tid]);
-    __syncthreads();
-    for (int off = DB / 2; off > 0; off >>= 1) {
-        if (tid < off) red[tid] += red[tid + off];
-        __syncthreads();
-    }
-    if (tid == 0) logdet_part[b * nblk + blk] = red[0];
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2a, blocked version: the 128x128 block is processed in four 32-column panels so the serial chain is
-// 128 short warp-level column steps (registers + one shared broadcast per column) instead of 256
-// CTA-wide barriers, and everything quadratic in the panel (SYRK inside the block, the off-diagonal
+// The block is processed in four 32-column panels so the serial chain is 128 short warp-level column steps
+// (registers + one shared broadcast per column; a column-at-a-time CTA-wide version with 256 barriers took
+// 211 us, this one 40 us), and everything quadratic in the panel (SYRK inside the block, the off-diagonal
 // blocks of the inverse) runs on DMMA over 8x8 output blocks spread across the 16 warps.
-//   L(i,j) = S[i][j] (j <= i);   T(i,j) = inv(L)(i,j) = S[j][i+1] (j <= i)   -- same packing as above.
-// ------------------------------------------------------------------------------------------------
+//   L(i,j) = S[i][j] (j <= i);   T(i,j) = inv(L)(i,j) = S[j][i+1] (j <= i).
 constexpr int SB = 32;                 // panel width inside the diagonal block
 constexpr int TLD = 65;                // row stride of the 64x64 scratch of the inverse recursion
 
@@ -981,30 +915,16 @@ void launch_grad_trace(const double* X, int64_t sX, int n, int dp, Hyper h, cons
     CUGP_CUDA(cudaGetLastError());
 }
 
-static int g_diag_variant = 1;  // 1: blocked (DMMA) kernel, 0: column-at-a-time kernel
-void set_diag_variant(int v) { g_diag_variant = v; }
-
 void launch_potrf_diag(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd, double* logdet_part,
                        int nblk, int blk, int batch, cudaStream_t st) {
-    if (g_diag_variant == 0) {
-        constexpr size_t smem = (size_t)DB * DLD * sizeof(double);
-        static bool configured = false;
-        if (!configured) {
-            CUGP_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
-        potrf_diag_kernel<<<batch, DIAG_THREADS, smem, st>>>(A, ld, sA, n, j0, invd + (int64_t)blk * DB * DB, sInvd,
-                                                             logdet_part, nblk, blk);
-    } else {
-        constexpr size_t smem = (size_t)(DB * DLD + 64 * TLD + DB + 2 * SB + DB) * sizeof(double);
-        static bool configured = false;
-        if (!configured) {
-            CUGP_CUDA(cudaFuncSetAttribute(potrf_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
-        potrf_diag_blocked_kernel<<<batch, DIAG_THREADS, smem, st>>>(A, ld, sA, n, j0, invd + (int64_t)blk * DB * DB,
-                                                                     sInvd, logdet_part, nblk, blk, 1, nullptr);
+    constexpr size_t smem = (size_t)(DB * DLD + 64 * TLD + DB + 2 * SB + DB) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        CUGP_CUDA(cudaFuncSetAttribute(potrf_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
     }
+    potrf_diag_blocked_kernel<<<batch, DIAG_THREADS, smem, st>>>(A, ld, sA, n, j0, invd + (int64_t)blk * DB * DB, sInvd,
+                                                                 logdet_part, nblk, blk, 1, nullptr);
     CUGP_CUDA(cudaGetLastError());
 }
 

@@ -46,7 +46,6 @@ void launch_potrf_diag(double* A, int64_t ld, int64_t sA, int n, int j0, double*
 void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* invd, int64_t sInvd, int batch,
                        cudaStream_t st);
 void debug_diag_phases(double* A, int64_t ld, int n, double* invd, double* logdet, long long* stamps_dev, cudaStream_t st);
-void set_diag_variant(int v);  // 1 (default): blocked DMMA kernel; 0: column-at-a-time kernel
 
 // ---- K3: alpha = L^-T z.  (The forward substitution is fused into the Cholesky, gp.cu.)
 // Blocked backward sweep L^T alpha = z (matrixops.cpp:156-164) with the stored inverses of the diagonal blocks;

@@ -51,8 +51,7 @@ long cugp_launch_count(void);
 void cugp_launch_count_reset(void);
 
 /* Tuning knobs (tests and benchmarks).  "potrf_nb": outer block width of the two-level blocked Cholesky, a multiple
- * of 128, 0 = choose by matrix size; "lookahead": 1/0 panel look-ahead on a second stream; "gemm_kernel": 1 = warp
- * specialised DMMA GEMM, 0 = cp.async GEMM; "diag_kernel": 1 = blocked diagonal-block kernel, 0 = column at a time. */
+ * of 128, 0 = choose by matrix size; "lookahead": 1/0 panel look-ahead on a second stream. */
 int cugp_set_tuning(const char *key, long value);
 
 /* ---- Covsum (cpp_serial_gp/covkernel.h:3-38) ------------------------------------------------------ */

@@ -18,7 +18,6 @@ for n in sizes:
     g = cg.Covsum(n, 10)
     g.set_data(X, y)
     for dv in variants:
-        L.cugp_set_tuning(b"diag_kernel", dv)
         for nb, la in [(nb, la) for nb in nbs for la in lookahead]:
             if nb > n:
                 continue

@@ -1,4 +1,4 @@
-"""A/B of the two GEMM kernels (tuning key gemm_kernel) on the probe shapes and on the Cholesky."""
+"""DMMA GEMM on the probe shapes next to the DMMA-only probe (burst and sustained)."""
 import ctypes as C
 import sys
 
@@ -6,8 +6,7 @@ sys.path.insert(0, ".")
 from cugp_b200._lib import lib
 
 L = lib()
-for v in (0, 1):
-    L.cugp_set_tuning(b"gemm_kernel", v)
+for v in (1,):
     for M, N, K in [(8192, 8192, 128), (8192, 8192, 512), (8192, 8192, 1024), (16384, 16384, 1024), (32768, 32768, 1024)]:
         t = C.c_double()
         rc = L.cugp_probe_gemm(M, N, K, 5, C.byref(t))
