@@ -247,15 +247,15 @@ GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(
     CUGP_CUDA(cudaMemsetAsync(invd, 0, (size_t)B * nblk * kDiag * kDiag * sizeof(double), st));  // upper triangles stay zero
     dalloc(logdet_part, (size_t)B * nblk);
     dalloc(work, bn);
-    dalloc(z, bn);
     dalloc(alpha, bn);
     dalloc(scal, (size_t)B * 4);
+    dalloc(tpart, trsv_backward_scratch(n, B));
     dalloc(gradout, (size_t)B * 3);
 }
 
 GpBatch::~GpBatch() {
     if (st) cudaStreamSynchronize(st);
-    dfree(X); dfree(y); dfree(Kb); dfree(invd); dfree(logdet_part); dfree(work); dfree(z); dfree(alpha); dfree(scal);
+    dfree(X); dfree(y); dfree(Kb); dfree(invd); dfree(logdet_part); dfree(work); dfree(alpha); dfree(scal);
     dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout); dfree(tpart);
     dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar);
     if (hstage) cudaFreeHost(hstage);
@@ -365,7 +365,6 @@ void GpBatch::solve() {
     } else {
         const int64_t sI = (int64_t)nblk * kDiag * kDiag;
         launch_copy_rows(zrow, mat_stride(), work, n, n, B, st);  // the sweep consumes its right-hand side
-        dalloc(tpart, trsv_backward_scratch(n, B));
         launch_trsv_backward(Kb, ld, mat_stride(), n, invd, sI, work, alpha, n, tpart, B, st);
         launches += 1 + nblk + 2 * (cdiv(n, 1024) - 1);
     }

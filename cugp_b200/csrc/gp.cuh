@@ -28,11 +28,11 @@ struct GpBatch {
     double* Kb = nullptr;                   // [B][n+1][ld]: K, then L in place; row n: y^T, then z^T = (L^-1 y)^T
     double* invd = nullptr;                 // [B][nblk][128][128] inverses of L's diagonal blocks
     double* logdet_part = nullptr;          // [B][nblk]
-    double *work = nullptr, *z = nullptr, *alpha = nullptr;  // [B][n]
+    double *work = nullptr, *alpha = nullptr;  // [B][n]
     double* scal = nullptr;                 // [B][4] quad, logdet, LL
     double *Tb = nullptr, *Wb = nullptr;    // [B][n][ld] lazily: T = L^-1 ; scratch, then Kinv (lower)
     double *gradpart = nullptr, *gradout = nullptr;
-    double* tpart = nullptr;                // partial sums of the backward sweep's panel launches (lazily)
+    double* tpart = nullptr;                // [B][8][n] partial sums of the backward sweep's panel launches
     // prediction workspace (lazily sized)
     double *Xt = nullptr, *Ks = nullptr, *meanpart = nullptr, *css = nullptr, *pmean = nullptr, *pvar = nullptr;
     int pred_cap = 0;
