@@ -51,9 +51,11 @@ int potrf_outer_width(int n) {
     }();
     const int forced = g_potrf_nb ? g_potrf_nb : env;
     if (forced >= kDiag) return forced / kDiag * kDiag;
+    // measured with look-ahead (profiles/r1_cholesky_nb_sweep.txt): wider panels only pay once the trailing update
+    // dominates the chain of diagonal blocks
     if (n >= 24576) return 1024;
-    if (n >= 6144) return 512;
-    if (n >= 3072) return 256;
+    if (n >= 9000) return 512;
+    if (n >= 5000) return 256;
     return kDiag;
 }
 
