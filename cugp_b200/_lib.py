@@ -15,6 +15,13 @@ dp = C.POINTER(C.c_double)
 EVAL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, dp, dp, dp)
 
 
+class ShardStreamStats(C.Structure):
+    """struct cugp_shardstream_stats (include/cugp.h)."""
+    _fields_ = [("passes", C.c_long), ("groups", C.c_long), ("shards_parsed", C.c_long), ("cache_hits", C.c_long),
+                ("parse_ms", C.c_double), ("reader_wait_ms", C.c_double), ("h2d_bytes", C.c_double),
+                ("cache_bytes", C.c_double)]
+
+
 class CugpError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"cugp error {code}: {msg}")
@@ -72,6 +79,18 @@ SIGNATURES = {
     "cugp_poe_finalize_dev": (C.c_int, [C.c_void_p, C.c_int, dp, dp]),
     "cugp_poe_finalize": (C.c_int, [dp, C.c_int, dp, dp]),
     "cugp_bcm_predict": (C.c_int, [C.c_void_p, dp, C.c_int, dp, dp]),
+    "cugp_shardstream_open_files": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cugp_shardstream_open_memory": (C.c_int, [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(C.c_void_p)]),
+    "cugp_shardstream_close": (C.c_int, [C.c_void_p]),
+    "cugp_shardstream_set_loghyper": (C.c_int, [C.c_void_p, dp]),
+    "cugp_shardstream_get_loghyper": (C.c_int, [C.c_void_p, dp]),
+    "cugp_shardstream_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cugp_shardstream_loglik_grad_local": (C.c_int, [C.c_void_p, C.c_int, dp, dp]),
+    "cugp_shardstream_predict_moments_dev": (C.c_int, [C.c_void_p, dp, C.c_int, C.c_void_p]),
+    "cugp_shardstream_predict_moments": (C.c_int, [C.c_void_p, dp, C.c_int, dp]),
+    "cugp_shardstream_get_stats": (C.c_int, [C.c_void_p, C.POINTER(ShardStreamStats)]),
     "cugp_probe_fp64_peak": (C.c_int, [C.c_float, dp, dp]),
     "cugp_probe_dmma": (C.c_int, [C.c_float, dp, dp]),
     "cugp_probe_gemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, dp]),

@@ -10,6 +10,7 @@
 #include <new>
 #include <vector>
 
+#include "capi_internal.h"
 #include "gp.cuh"
 #include "optim.h"
 
@@ -31,24 +32,7 @@ void set_last_error(const char* fmt, ...) {
 
 using namespace cugp;
 
-#define CUGP_TRY try {
-#define CUGP_CATCH                                                                                          \
-    }                                                                                                       \
-    catch (const CudaError& e) {                                                                            \
-        set_last_error("CUDA error %d (%s) at %s:%d", (int)e.code, cudaGetErrorString(e.code), e.file, e.line); \
-        cudaGetLastError();                                                                                 \
-        return e.code == cudaErrorMemoryAllocation ? CUGP_ERR_NOMEM : CUGP_ERR_CUDA;                        \
-    }                                                                                                       \
-    catch (const std::bad_alloc&) {                                                                         \
-        set_last_error("host allocation failed");                                                           \
-        return CUGP_ERR_NOMEM;                                                                              \
-    }                                                                                                       \
-    catch (...) {                                                                                           \
-        set_last_error("unexpected exception");                                                             \
-        return CUGP_ERR_CUDA;                                                                               \
-    }
-
-static int require_device() {
+int require_device() {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count <= 0) {
@@ -72,8 +56,8 @@ static std::vector<GpBatch*>& live_batches() {
     static std::vector<GpBatch*> v;
     return v;
 }
-static void track(GpBatch* g) { live_batches().push_back(g); }
-static void untrack(GpBatch* g) {
+void track(GpBatch* g) { live_batches().push_back(g); }
+void untrack(GpBatch* g) {
     auto& v = live_batches();
     g_launch_base += g->launches;
     v.erase(std::remove(v.begin(), v.end(), g), v.end());
@@ -140,6 +124,14 @@ int cugp_set_tuning(const char* key, long value) {
     }
     if (std::strcmp(key, "lookahead") == 0) {
         set_lookahead(value != 0);
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "gemm_tpc") == 0) {
+        if (value < 0 || value > 64) {
+            set_last_error("gemm_tpc must be 0 (auto) or 1..64");
+            return CUGP_ERR_INVALID;
+        }
+        set_gemm_tiles_per_cta((int)value);
         return CUGP_OK;
     }
     set_last_error("unknown tuning key '%s'", key);

@@ -141,6 +141,49 @@ __device__ __forceinline__ void produce_operand(double* smem, const double* __re
     }
 }
 
+// Geometry of one output tile of the launch (tile index t in raster order, batch index b).
+struct TileGeom {
+    int ti, m0, n0, k_lo, nk, k_hi;
+    int64_t offA, offB, offC, b;
+};
+
+template <int BM, int BN>
+__device__ __forceinline__ TileGeom tile_geom(const GemmParams& p, int64_t t, int tiles_m, int tiles_n) {
+    TileGeom g;
+    // consecutive work items walk the raster order of one matrix, then the next batch entry
+    g.b = t / p.tiles_per_mat;
+    int ti, tj;
+    raster_tile((int)(t - g.b * p.tiles_per_mat), tiles_m, tiles_n, p.lower_tiles != 0, ti, tj);
+    g.ti = ti;
+    g.m0 = ti * BM;
+    g.n0 = tj * BN;
+    if (p.batch_inner > 1) {
+        const int64_t bi = g.b % p.batch_inner, bo = g.b / p.batch_inner;
+        g.offA = bi * p.sA + bo * p.sA2;
+        g.offB = bi * p.sB + bo * p.sB2;
+        g.offC = bi * p.sC + bo * p.sC2;
+    } else {
+        g.offA = g.b * p.sA;
+        g.offB = g.b * p.sB;
+        g.offC = g.b * p.sC;
+    }
+    int k_lo = 0, k_hi = p.K;
+    if (p.klo_ti) k_lo = max(k_lo, g.m0);
+    if (p.klo_tj) k_lo = max(k_lo, g.n0);
+    if (p.khi_ti) k_hi = min(k_hi, g.m0 + BM);
+    if (p.khi_tj) k_hi = min(k_hi, g.n0 + BN);
+    g.k_lo = k_lo;
+    g.k_hi = k_hi;
+    g.nk = k_hi > k_lo ? (k_hi - k_lo + WBK - 1) / WBK : 0;
+    return g;
+}
+
+// Each CTA owns `tiles_per_cta` consecutive tiles of the raster order and walks them with ONE running stage
+// counter: the producer warp group is never more than NSTAGE stages ahead of the math warps but it does not stop at
+// a tile boundary, so the next tile's first stages (and its C tile, prefetched into L2) are in flight while the
+// math warps run the epilogue of the current one -- the pipeline fill and most of the epilogue latency are paid
+// once per CTA instead of once per tile.  The count stays small (<= 8) so CTAs keep retiring every few hundred
+// microseconds and the high-priority panel stream of the look-ahead Cholesky still finds free SMs.
 template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_kernel(const GemmParams p) {
     constexpr int NCW = WARPS_M * WARPS_N;  // consumer warps
@@ -151,35 +194,14 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + NSTAGE * A_SZ;
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + NSTAGE * (A_SZ + B_SZ));
+    double* red = smem + NSTAGE * (A_SZ + B_SZ);  // [WARPS_M][BN] scratch of the colsumsq epilogue
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(red + WARPS_M * BN);
     unsigned long long* empty = full + NSTAGE;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-    int ti, tj;
-    raster_tile(blockIdx.x, tiles_m, tiles_n, p.lower_tiles != 0, ti, tj);
-    const int m0 = ti * BM, n0 = tj * BN;
-    const int64_t b = blockIdx.y;
-    int64_t offA, offB, offC;
-    if (p.batch_inner > 1) {
-        const int64_t bi = b % p.batch_inner, bo = b / p.batch_inner;
-        offA = bi * p.sA + bo * p.sA2;
-        offB = bi * p.sB + bo * p.sB2;
-        offC = bi * p.sC + bo * p.sC2;
-    } else {
-        offA = b * p.sA;
-        offB = b * p.sB;
-        offC = b * p.sC;
-    }
-    const double* __restrict__ A = p.A + offA;
-    const double* __restrict__ B = p.B + offB;
-
-    int k_lo = 0, k_hi = p.K;
-    if (p.klo_ti) k_lo = max(k_lo, m0);
-    if (p.klo_tj) k_lo = max(k_lo, n0);
-    if (p.khi_ti) k_hi = min(k_hi, m0 + BM);
-    if (p.khi_tj) k_hi = min(k_hi, n0 + BN);
-    const int nk = k_hi > k_lo ? (k_hi - k_lo + WBK - 1) / WBK : 0;
+    const int64_t t_begin = (int64_t)blockIdx.x * p.tiles_per_cta;
+    const int64_t t_end = min(t_begin + p.tiles_per_cta, p.tiles_per_mat * (int64_t)p.batch);
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) {
@@ -197,22 +219,28 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
         // ------------------------------ producer warp(s) ------------------------------
         if (kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
         const int pl = tid - NCW * 32;  // producer lane
-        for (int kt = 0; kt < nk; kt++) {
-            const int s = kt % NSTAGE;
-            if (kt >= NSTAGE) mbar_wait(&empty[s], (unsigned)((kt / NSTAGE - 1) & 1));
-            const int k0 = k_lo + kt * WBK;
-            produce_operand<BM, A_KC>(As + s * A_SZ, A, p.lda, m0, p.M, k0, k_hi, pl);
-            produce_operand<BN, B_KC>(Bs + s * B_SZ, B, p.ldb, n0, p.N, k0, k_hi, pl);
-            cp_async_arrive_noinc(&full[s]);  // this lane's arrival fires when its copies above have landed
-        }
-        if (p.beta != 0.0 && !p.colsumsq) {
-            // All stages are issued: pull the C tile into L2 now, NSTAGE stages ahead of the epilogue that reads it
-            // (prefetching at kernel start had the lines evicted again before use: DRAM read C twice).
-            const double* C = p.C + offC;
-            const int rows = min(BM, p.M - m0), cols = min(BN, p.N - n0);
-            for (int r = pl; r < rows; r += NPW * 32) {
-                const double* row = C + (int64_t)(m0 + r) * p.ldc + n0;
-                for (int c = 0; c < cols; c += 16) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + c));
+        unsigned it = 0;                // stages issued by this CTA so far (all tiles)
+        for (int64_t t = t_begin; t < t_end; t++) {
+            const TileGeom g = tile_geom<BM, BN>(p, t, tiles_m, tiles_n);
+            const double* __restrict__ A = p.A + g.offA;
+            const double* __restrict__ B = p.B + g.offB;
+            for (int kt = 0; kt < g.nk; kt++, it++) {
+                const unsigned s = it % NSTAGE;
+                if (it >= NSTAGE) mbar_wait(&empty[s], (it / NSTAGE - 1) & 1);
+                const int k0 = g.k_lo + kt * WBK;
+                produce_operand<BM, A_KC>(As + s * A_SZ, A, p.lda, g.m0, p.M, k0, g.k_hi, pl);
+                produce_operand<BN, B_KC>(Bs + s * B_SZ, B, p.ldb, g.n0, p.N, k0, g.k_hi, pl);
+                cp_async_arrive_noinc(&full[s]);  // this lane's arrival fires when its copies above have landed
+            }
+            if (p.beta != 0.0 && !p.colsumsq) {
+                // All stages of the tile are issued: pull its C tile into L2 now, NSTAGE stages ahead of the epilogue
+                // that reads it (prefetching at kernel start had the lines evicted again before use: DRAM read C twice).
+                const double* C = p.C + g.offC;
+                const int rows = min(BM, p.M - g.m0), cols = min(BN, p.N - g.n0);
+                for (int r = pl; r < rows; r += NPW * 32) {
+                    const double* row = C + (int64_t)(g.m0 + r) * p.ldc + g.n0;
+                    for (int c = 0; c < cols; c += 16) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(row + c));
+                }
             }
         }
         cp_async_wait<0>();
@@ -223,140 +251,147 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
     if (kRegSplit) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
     const int g = lane >> 2, q = lane & 3;
     const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
-    double acc[MI][NI][2];
+    unsigned it = 0;
+    for (int64_t t = t_begin; t < t_end; t++) {
+        const TileGeom tg = tile_geom<BM, BN>(p, t, tiles_m, tiles_n);
+        const int m0 = tg.m0, n0 = tg.n0;
+        double acc[MI][NI][2];
 #pragma unroll
-    for (int i = 0; i < MI; i++)
+        for (int i = 0; i < MI; i++)
 #pragma unroll
-        for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int kt = 0; kt < nk; kt++) {
-        const int s = kt % NSTAGE;
-        mbar_wait(&full[s], (unsigned)((kt / NSTAGE) & 1));
-        const double* as = As + s * A_SZ;
-        const double* bs = Bs + s * B_SZ;
+        for (int kt = 0; kt < tg.nk; kt++, it++) {
+            const unsigned s = it % NSTAGE;
+            mbar_wait(&full[s], (it / NSTAGE) & 1);
+            const double* as = As + s * A_SZ;
+            const double* bs = Bs + s * B_SZ;
 #pragma unroll
-        for (int kk = 0; kk < WBK; kk += 4) {
-            double af[MI], bf[NI];
+            for (int kk = 0; kk < WBK; kk += 4) {
+                double af[MI], bf[NI];
 #pragma unroll
-            for (int i = 0; i < MI; i++)
-                af[i] = A_KC ? as[(wm0 + i * 8 + g) * (WBK + WPAD) + kk + q] : as[(kk + q) * (BM + WPAD) + wm0 + i * 8 + g];
+                for (int i = 0; i < MI; i++)
+                    af[i] = A_KC ? as[(wm0 + i * 8 + g) * (WBK + WPAD) + kk + q] : as[(kk + q) * (BM + WPAD) + wm0 + i * 8 + g];
 #pragma unroll
-            for (int j = 0; j < NI; j++)
-                bf[j] = B_KC ? bs[(wn0 + j * 8 + g) * (WBK + WPAD) + kk + q] : bs[(kk + q) * (BN + WPAD) + wn0 + j * 8 + g];
+                for (int j = 0; j < NI; j++)
+                    bf[j] = B_KC ? bs[(wn0 + j * 8 + g) * (WBK + WPAD) + kk + q] : bs[(kk + q) * (BN + WPAD) + wn0 + j * 8 + g];
 #pragma unroll
-            for (int i = 0; i < MI; i++)
+                for (int i = 0; i < MI; i++)
 #pragma unroll
-                for (int j = 0; j < NI; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                    for (int j = 0; j < NI; j++) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
-    }
 
-    if (p.colsumsq) {
-        // Epilogue for the predictive variance: sum over this tile's rows of (alpha*acc)^2, per column.
-        asm volatile("bar.sync 1, %0;\n" ::"n"(NCW * 32) : "memory");  // all consumers are done with the stages
-        double* red = smem;  // [WARPS_M][BN]
+        if (p.colsumsq) {
+            // Epilogue for the predictive variance: sum over this tile's rows of (alpha*acc)^2, per column.
 #pragma unroll
-        for (int j = 0; j < NI; j++) {
-            double s0 = 0.0, s1 = 0.0;
+            for (int j = 0; j < NI; j++) {
+                double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-            for (int i = 0; i < MI; i++) {
-                int row = m0 + wm0 + i * 8 + g;
-                if (row < p.M) {
-                    double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-                    s0 += v0 * v0;
-                    s1 += v1 * v1;
+                for (int i = 0; i < MI; i++) {
+                    int row = m0 + wm0 + i * 8 + g;
+                    if (row < p.M) {
+                        double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+                        s0 += v0 * v0;
+                        s1 += v1 * v1;
+                    }
+                }
+#pragma unroll
+                for (int off = 4; off < 32; off <<= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                }
+                if (g == 0) {
+                    red[(warp / WARPS_N) * BN + wn0 + j * 8 + 2 * q] = s0;
+                    red[(warp / WARPS_N) * BN + wn0 + j * 8 + 2 * q + 1] = s1;
                 }
             }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(NCW * 32) : "memory");
+            double* out = p.colsumsq + tg.b * p.sCss + (int64_t)tg.ti * p.N;
+            for (int c = tid; c < BN; c += NCW * 32) {
+                if (n0 + c < p.N) {
+                    double s = 0.0;
 #pragma unroll
-            for (int off = 4; off < 32; off <<= 1) {
-                s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                    for (int w = 0; w < WARPS_M; w++) s += red[w * BN + c];
+                    out[n0 + c] = s;
+                }
             }
-            if (g == 0) {
-                red[(warp / WARPS_N) * BN + wn0 + j * 8 + 2 * q] = s0;
-                red[(warp / WARPS_N) * BN + wn0 + j * 8 + 2 * q + 1] = s1;
-            }
+            asm volatile("bar.sync 1, %0;\n" ::"n"(NCW * 32) : "memory");  // red is reused by the next tile
+            continue;
         }
-        asm volatile("bar.sync 1, %0;\n" ::"n"(NCW * 32) : "memory");
-        double* out = p.colsumsq + b * p.sCss + (int64_t)ti * p.N;
-        for (int c = tid; c < BN; c += NCW * 32) {
-            if (n0 + c < p.N) {
-                double s = 0.0;
-#pragma unroll
-                for (int w = 0; w < WARPS_M; w++) s += red[w * BN + c];
-                out[n0 + c] = s;
-            }
-        }
-        return;
-    }
 
-    double* __restrict__ C = p.C + offC;
-    const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    const bool interior = vec_ok && (m0 + BM <= p.M) && (n0 + BN <= p.N);
-    if (interior) {
-        // All loads of a batch are issued before the first use: one L2 round trip per batch instead of one per
-        // element pair (a load placed after a store to the same array cannot be hoisted by the compiler).
-        constexpr int IB = MI >= 4 ? 4 : MI;
-        double* base = C + (int64_t)(m0 + wm0 + g) * p.ldc + n0 + wn0 + 2 * q;
+        double* __restrict__ C = p.C + tg.offC;
+        const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        const bool interior = vec_ok && (m0 + BM <= p.M) && (n0 + BN <= p.N);
+        if (interior) {
+            // All loads of a batch are issued before the first use: one L2 round trip per batch instead of one per
+            // element pair (a load placed after a store to the same array cannot be hoisted by the compiler).
+            constexpr int IB = MI >= 4 ? 4 : MI;
+            double* base = C + (int64_t)(m0 + wm0 + g) * p.ldc + n0 + wn0 + 2 * q;
 #pragma unroll
-        for (int i0 = 0; i0 < MI; i0 += IB) {
-            double2 old[IB][NI];
-            if (p.beta != 0.0) {
+            for (int i0 = 0; i0 < MI; i0 += IB) {
+                double2 old[IB][NI];
+                if (p.beta != 0.0) {
+#pragma unroll
+                    for (int i = 0; i < IB; i++)
+#pragma unroll
+                        for (int j = 0; j < NI; j++)
+                            old[i][j] = *reinterpret_cast<const double2*>(base + (int64_t)(i0 + i) * 8 * p.ldc + j * 8);
+                }
 #pragma unroll
                 for (int i = 0; i < IB; i++)
 #pragma unroll
-                    for (int j = 0; j < NI; j++)
-                        old[i][j] = *reinterpret_cast<const double2*>(base + (int64_t)(i0 + i) * 8 * p.ldc + j * 8);
-            }
-#pragma unroll
-            for (int i = 0; i < IB; i++)
-#pragma unroll
-                for (int j = 0; j < NI; j++) {
-                    double v0 = p.alpha * acc[i0 + i][j][0], v1 = p.alpha * acc[i0 + i][j][1];
-                    if (p.beta != 0.0) {
-                        v0 += p.beta * old[i][j].x;
-                        v1 += p.beta * old[i][j].y;
+                    for (int j = 0; j < NI; j++) {
+                        double v0 = p.alpha * acc[i0 + i][j][0], v1 = p.alpha * acc[i0 + i][j][1];
+                        if (p.beta != 0.0) {
+                            v0 += p.beta * old[i][j].x;
+                            v1 += p.beta * old[i][j].y;
+                        }
+                        *reinterpret_cast<double2*>(base + (int64_t)(i0 + i) * 8 * p.ldc + j * 8) = make_double2(v0, v1);
                     }
-                    *reinterpret_cast<double2*>(base + (int64_t)(i0 + i) * 8 * p.ldc + j * 8) = make_double2(v0, v1);
-                }
+            }
+            continue;
         }
-        return;
-    }
 #pragma unroll
-    for (int i = 0; i < MI; i++) {
-        int row = m0 + wm0 + i * 8 + g;
-        if (row >= p.M) continue;
+        for (int i = 0; i < MI; i++) {
+            int row = m0 + wm0 + i * 8 + g;
+            if (row >= p.M) continue;
 #pragma unroll
-        for (int j = 0; j < NI; j++) {
-            int col = n0 + wn0 + j * 8 + 2 * q;
-            if (col >= p.N) continue;
-            double* cp = C + (int64_t)row * p.ldc + col;
-            double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-            if (col + 1 < p.N && vec_ok) {
-                if (p.beta != 0.0) {
-                    double2 old = *reinterpret_cast<const double2*>(cp);
-                    v0 += p.beta * old.x;
-                    v1 += p.beta * old.y;
-                }
-                *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
-            } else {
-                if (p.beta != 0.0) v0 += p.beta * cp[0];
-                cp[0] = v0;
-                if (col + 1 < p.N) {
-                    if (p.beta != 0.0) v1 += p.beta * cp[1];
-                    cp[1] = v1;
+            for (int j = 0; j < NI; j++) {
+                int col = n0 + wn0 + j * 8 + 2 * q;
+                if (col >= p.N) continue;
+                double* cp = C + (int64_t)row * p.ldc + col;
+                double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+                if (col + 1 < p.N && vec_ok) {
+                    if (p.beta != 0.0) {
+                        double2 old = *reinterpret_cast<const double2*>(cp);
+                        v0 += p.beta * old.x;
+                        v1 += p.beta * old.y;
+                    }
+                    *reinterpret_cast<double2*>(cp) = make_double2(v0, v1);
+                } else {
+                    if (p.beta != 0.0) v0 += p.beta * cp[0];
+                    cp[0] = v0;
+                    if (col + 1 < p.N) {
+                        if (p.beta != 0.0) v1 += p.beta * cp[1];
+                        cp[1] = v1;
+                    }
                 }
             }
         }
     }
 }
 
+static int g_tiles_per_cta = 0;  // 0: by grid size; otherwise forced (cugp_set_tuning("gemm_tpc", v))
+
 template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC>
-void launch_ws(const GemmParams& p, cudaStream_t stream) {
+void launch_ws(const GemmParams& p_in, cudaStream_t stream) {
     constexpr int NT = (WARPS_M * WARPS_N + NPW) * 32;
     constexpr size_t smem =
-        (size_t)NSTAGE * (ws_tile_doubles<BM, A_KC>() + ws_tile_doubles<BN, B_KC>()) * sizeof(double) + 2 * NSTAGE * 8;
+        (size_t)(NSTAGE * (ws_tile_doubles<BM, A_KC>() + ws_tile_doubles<BN, B_KC>()) + WARPS_M * BN) * sizeof(double) +
+        2 * NSTAGE * 8;
     static_assert(smem <= 227 * 1024, "stage buffers exceed shared memory");
     static bool configured = false;
     auto kern = dgemm_ws_kernel<BM, BN, WARPS_M, WARPS_N, NSTAGE, A_KC, B_KC>;
@@ -364,6 +399,7 @@ void launch_ws(const GemmParams& p, cudaStream_t stream) {
         CUGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    GemmParams p = p_in;
     int tiles_m = cdiv(p.M, BM), tiles_n = cdiv(p.N, BN);
     int64_t tiles = (int64_t)tiles_m * tiles_n;
     if (p.lower_tiles) {
@@ -371,7 +407,16 @@ void launch_ws(const GemmParams& p, cudaStream_t stream) {
         tiles = (int64_t)tiles_n * (tiles_n + 1) / 2 + (int64_t)(tiles_m - tiles_n) * tiles_n;
     }
     if (tiles <= 0 || p.batch <= 0) return;
-    dim3 grid((unsigned)tiles, (unsigned)p.batch);
+    const int64_t total = tiles * p.batch;
+    // several tiles per CTA only once the grid is many waves deep: the chain keeps the SM's pipeline full across
+    // tile boundaries, but fewer, longer CTAs must not leave SMs idle in the last wave
+    int tpc = g_tiles_per_cta;
+    // (measured, profiles/r1_gemm_tpc_sweep.txt: 8192^2 x 1024 probe 34.1 -> 34.6 TFLOP/s, 32768^2 34.6 -> 35.0 at 4 tiles
+    // per CTA; the n = 10 000 Cholesky loses 7 % at 2 because its look-ahead panel stream then waits for SMs)
+    if (tpc <= 0) tpc = total >= 148 * 512 ? 8 : total >= 148 * 96 ? 4 : total >= 148 * 40 ? 2 : 1;
+    p.tiles_per_mat = tiles;
+    p.tiles_per_cta = tpc;
+    dim3 grid((unsigned)((total + tpc - 1) / tpc));
     kern<<<grid, NT, smem, stream>>>(p);
     CUGP_CUDA(cudaGetLastError());
 }
@@ -385,6 +430,8 @@ void launch_layout(const GemmParams& p, bool a_kc, bool b_kc, cudaStream_t strea
 }
 
 }  // namespace
+
+void set_gemm_tiles_per_cta(int v) { g_tiles_per_cta = v; }
 
 int gemm_tile_m(GemmConfig cfg) { return cfg == GEMM_BIG ? 128 : 64; }
 

@@ -31,6 +31,8 @@ struct GemmParams {
     int khi_ti, khi_tj;      // restrict k <  (ti+1)*BM / (tj+1)*BN
     double* colsumsq;        // non-null: write per-row-tile column sums of squares [tiles_m][N] instead of C
     int64_t sCss;            // batch stride of colsumsq
+    int64_t tiles_per_mat;   // filled by the launcher: output tiles of one matrix (raster order)
+    int tiles_per_cta;       // filled by the launcher: consecutive work items (tile, batch) one CTA walks
 };
 
 enum GemmConfig { GEMM_BIG = 0, GEMM_TALL = 1, GEMM_SMALL = 2 };
@@ -40,5 +42,7 @@ void launch_gemm(const GemmParams& p, bool a_kc, bool b_kc, GemmConfig cfg, cuda
 // Picks BIG when the grid fills the chip, SMALL otherwise.
 GemmConfig pick_config(int M, int N, int batch, bool lower_tiles);
 int gemm_tile_m(GemmConfig cfg);
+// Tuning: tiles walked per CTA (0 = by grid size).
+void set_gemm_tiles_per_cta(int v);
 
 }  // namespace cugp

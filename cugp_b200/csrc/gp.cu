@@ -225,7 +225,7 @@ void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t 
 // ------------------------------------------------------------------------------------------------
 // GpBatch
 // ------------------------------------------------------------------------------------------------
-GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(d_) {
+GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(d_), Bcap(B_) {
     dp = (int)round_up(d, 2);
     h = make_hyper(theta);
     ld = padded_ld(n);
@@ -261,8 +261,10 @@ GpBatch::~GpBatch() {
     dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout); dfree(tpart);
     dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar);
     if (hstage) cudaFreeHost(hstage);
+    if (hres) cudaFreeHost(hres);
     for (cudaEvent_t e : prof.ev) cudaEventDestroy(e);
     for (cudaEvent_t e : la.ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : bwd_ev) cudaEventDestroy(e);
     if (la.st2) {
         cudaStreamSynchronize(la.st2);
         cudaStreamDestroy(la.st2);
@@ -300,6 +302,44 @@ void GpBatch::set_data(const double* Xh, const double* yh) {
     CUGP_CUDA(cudaMemcpyAsync(y, s + rows * dp, rows * sizeof(double), cudaMemcpyHostToDevice, st));
     have_data = true;
     invalidate();
+}
+
+void GpBatch::set_active(int b) {
+    if (b < 1 || b > Bcap) throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};
+    if (b != B) {
+        B = b;
+        invalidate();
+    }
+}
+
+void GpBatch::adopt_device_data(const double* Xd, const double* yd, int b, cudaEvent_t ready) {
+    set_active(b);
+    if (ready) CUGP_CUDA(cudaStreamWaitEvent(st, ready, 0));
+    const size_t rows = (size_t)b * n;
+    CUGP_CUDA(cudaMemcpyAsync(X, Xd, rows * dp * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CUGP_CUDA(cudaMemcpyAsync(y, yd, rows * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    have_data = true;
+    invalidate();
+}
+
+void GpBatch::eval_launch(bool want_grad) {
+    if (!hres) CUGP_CUDA(cudaMallocHost((void**)&hres, (size_t)Bcap * 8 * sizeof(double)));
+    factorize();
+    CUGP_CUDA(cudaMemcpyAsync(hres, scal, (size_t)B * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (want_grad) {
+        gradient_launch();
+        CUGP_CUDA(cudaMemcpyAsync(hres + (size_t)Bcap * 4, gradout, (size_t)B * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    eval_grad = want_grad;
+}
+
+void GpBatch::eval_collect(double* ll_out, double* g_out) {
+    sync();
+    for (int b = 0; b < B; b++) {
+        if (ll_out) ll_out[b] = hres[(size_t)b * 4 + 2];
+        if (g_out)
+            for (int k = 0; k < 3; k++) g_out[(size_t)b * 3 + k] = eval_grad ? hres[(size_t)Bcap * 4 + (size_t)b * 3 + k] : 0.0;
+    }
 }
 
 void GpBatch::set_theta(const double th[3]) {
@@ -367,15 +407,22 @@ void GpBatch::solve() {
     } else {
         const int64_t sI = (int64_t)nblk * kDiag * kDiag;
         launch_copy_rows(zrow, mat_stride(), work, n, n, B, st);  // the sweep consumes its right-hand side
-        launch_trsv_backward(Kb, ld, mat_stride(), n, invd, sI, work, alpha, n, tpart, B, st);
+        const int nev = trsv_backward_events(n);
+        while ((int)bwd_ev.size() < nev) {
+            cudaEvent_t e;
+            CUGP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            bwd_ev.push_back(e);
+        }
+        launch_trsv_backward(Kb, ld, mat_stride(), n, invd, sI, work, alpha, n, tpart, B, st,
+                             lookahead_enabled() ? la.st2 : nullptr, bwd_ev.data(), nev);
         launches += 1 + nblk + 2 * (cdiv(n, 1024) - 1);
     }
     have_alpha = true;
 }
 
 void GpBatch::ensure_TW() {
-    dalloc(Tb, (size_t)B * (n + 1) * ld);  // same batch stride as Kb
-    dalloc(Wb, (size_t)B * (n + 1) * ld);
+    dalloc(Tb, (size_t)Bcap * (n + 1) * ld);  // same batch stride as Kb
+    dalloc(Wb, (size_t)Bcap * (n + 1) * ld);
 }
 
 void GpBatch::trtri() {
@@ -416,13 +463,17 @@ void GpBatch::loglik(double* ll_out) {
     for (int b = 0; b < B; b++) ll_out[b] = s[(size_t)b * 4 + 2];
 }
 
-void GpBatch::gradient(double* g_out) {
+void GpBatch::gradient_launch() {
     trtri();   // before solve(): alpha then is a single pass over T
     solve();
     lauum();
-    dalloc(gradpart, grad_trace_partials(n, B));
+    dalloc(gradpart, grad_trace_partials(n, Bcap));
     launch_grad_trace(X, (int64_t)n * dp, n, dp, h, Wb, ld, mat_stride(), alpha, n, gradpart, gradout, B, st);
     launches += 2;
+}
+
+void GpBatch::gradient(double* g_out) {
+    gradient_launch();
     CUGP_CUDA(cudaMemcpyAsync(g_out, gradout, (size_t)B * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     sync();
 }
@@ -439,11 +490,11 @@ void GpBatch::ensure_pred(int mc) {
     dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar);
     const size_t tiles64 = (size_t)cdiv(n, 64);
     dalloc(Xt, (size_t)mc * dp);
-    dalloc(Ks, (size_t)B * mc * ld);
-    dalloc(meanpart, (size_t)B * tiles64 * mc);
-    dalloc(css, (size_t)B * tiles64 * mc);
-    dalloc(pmean, (size_t)B * mc);
-    dalloc(pvar, (size_t)B * mc);
+    dalloc(Ks, (size_t)Bcap * mc * ld);
+    dalloc(meanpart, (size_t)Bcap * tiles64 * mc);
+    dalloc(css, (size_t)Bcap * tiles64 * mc);
+    dalloc(pmean, (size_t)Bcap * mc);
+    dalloc(pvar, (size_t)Bcap * mc);
     pred_cap = mc;
 }
 
@@ -455,7 +506,7 @@ void GpBatch::predict(const double* Xt_h, int m, double* mean_h, double* var_h, 
     trtri();
     solve();
     // chunk the test set so Kstar stays near 2 GB
-    int64_t cap = (int64_t)(2.0e9 / ((double)B * ld * 8.0));
+    int64_t cap = (int64_t)(2.0e9 / ((double)Bcap * ld * 8.0));
     int mc = (int)std::min<int64_t>(m, std::max<int64_t>(64, cap / 64 * 64));
     ensure_pred(mc);
     const int tiles_j = cdiv(n, kCovTile);

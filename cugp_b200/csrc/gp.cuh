@@ -18,7 +18,8 @@ struct PotrfLookahead {
 };
 
 struct GpBatch {
-    int B = 0, n = 0, d = 0, dp = 0, nblk = 0;
+    int B = 0, n = 0, d = 0, dp = 0, nblk = 0;  // B: GPs the launches carry (<= Bcap, see set_active)
+    int Bcap = 0;                               // GPs the buffers are sized for
     int64_t ld = 0;
     cudaStream_t st = nullptr;
     bool own_stream = false;
@@ -39,6 +40,8 @@ struct GpBatch {
     // pinned host staging
     double* hstage = nullptr;
     size_t hstage_bytes = 0;
+    double* hres = nullptr;                 // pinned [Bcap][8]: results of eval_launch
+    bool eval_grad = false;
 
     double theta[3] = {0, 0, 0};
     Hyper h{};
@@ -53,6 +56,7 @@ struct GpBatch {
         long count = 0;
     } prof;
     PotrfLookahead la;
+    std::vector<cudaEvent_t> bwd_ev;       // events of the overlapped backward sweep
     void prof_begin();                     // reset counters (events are reused)
     void prof_collect(double* ms, double* flops, long* count);
 
@@ -63,6 +67,14 @@ struct GpBatch {
 
     // X: B*n rows of d doubles (host, tight), y: B*n.  Packs to the padded device layout.
     void set_data(const double* Xh, const double* yh);
+    // Shard streaming: take the next group's packed data ([b][n][dp] inputs, [b][n] labels) from a device
+    // staging buffer filled by a copy stream; `ready` is the event recorded after that copy.  b <= Bcap GPs become active.
+    void adopt_device_data(const double* Xd, const double* yd, int b, cudaEvent_t ready);
+    void set_active(int b);                 // 1 <= b <= Bcap; invalidates
+    // One (LL [, gradient]) evaluation without a host wait: everything is queued on the stream and the results land in
+    // the pinned staging buffer; eval_collect() waits and hands out [B] log-likelihoods and [B][3] gradients.
+    void eval_launch(bool want_grad);
+    void eval_collect(double* ll_out, double* g_out);
     void set_theta(const double th[3]);
     void invalidate() { have_L = have_alpha = have_T = have_Kinv = false; }
 
@@ -75,6 +87,7 @@ struct GpBatch {
     void lauum();                           // Kinv (lower) = T^T T into Wb (cached)
     void loglik(double* ll_out);            // [B] host
     void scalars(double* out4);             // [B][4] host: quad, logdet, LL, 0
+    void gradient_launch();                 // queue trtri, alpha, lauum and the fused trace (gradout on the device)
     void gradient(double* g_out);           // [B][3] host, d(-LL)/dtheta
     void predict(const double* Xt_h, int m, double* mean_h, double* var_h, double* PQ_dev, int accumulate);
     void get_alpha(double* out);            // [B][n] host

@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(TRSV_THREADS)
 constexpr int BWD_PANEL = 1024;
 constexpr int BWD_PCOLS = 128, BWD_PROWS = 128, BWD_PCHUNKS = BWD_PANEL / BWD_PROWS;
 __global__ void __launch_bounds__(TRSV_THREADS)
-    trsv_bwd_panel_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int P0, int rows,
+    trsv_bwd_panel_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int P0, int rows, int c_lo, int c_hi,
                           const double* __restrict__ alpha, int64_t sVec, double* partial, int64_t sPart, int n) {
     __shared__ double ap[BWD_PROWS];
     __shared__ double red[4][BWD_PCOLS];
@@ -684,17 +684,17 @@ __global__ void __launch_bounds__(TRSV_THREADS)
     const int r0 = blockIdx.y * BWD_PROWS;                 // first row of this chunk inside the panel
     if (tid < BWD_PROWS) ap[tid] = (r0 + tid < rows) ? alpha[P0 + r0 + tid] : 0.0;
     const int cp = tid & 63, rg = tid >> 6;                // column pair, row group (32 rows each)
-    const int c = blockIdx.x * BWD_PCOLS + cp * 2;
+    const int c = c_lo + blockIdx.x * BWD_PCOLS + cp * 2;   // c_lo, c_hi even: a column pair never straddles c_hi
     double a0 = 0.0, a1 = 0.0;
     double2 v[32];
-    if (c < P0) {
+    if (c < c_hi) {
         const double* src = L + (int64_t)(P0 + r0 + rg * 32) * ld + c;
 #pragma unroll
         for (int u = 0; u < 32; u++)
             v[u] = (r0 + rg * 32 + u < rows) ? *reinterpret_cast<const double2*>(src + (int64_t)u * ld) : make_double2(0.0, 0.0);
     }
     __syncthreads();
-    if (c < P0) {
+    if (c < c_hi) {
 #pragma unroll
         for (int u = 0; u < 32; u++) {
             a0 += v[u].x * ap[rg * 32 + u];
@@ -705,15 +705,15 @@ __global__ void __launch_bounds__(TRSV_THREADS)
     red[rg][cp * 2 + 1] = a1;
     __syncthreads();
     if (tid < BWD_PCOLS) {
-        const int cc = blockIdx.x * BWD_PCOLS + tid;
-        if (cc < P0) partial[cc] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+        const int cc = c_lo + blockIdx.x * BWD_PCOLS + tid;
+        if (cc < c_hi) partial[cc] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
     }
 }
 
-__global__ void trsv_bwd_panel_reduce_kernel(const double* partial, int64_t sPart, int n, int chunks, int P0, double* work,
-                                             int64_t sVec) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P0) return;
+__global__ void trsv_bwd_panel_reduce_kernel(const double* partial, int64_t sPart, int n, int chunks, int c_lo, int c_hi,
+                                             double* work, int64_t sVec) {
+    const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_hi) return;
     const double* p = partial + (int64_t)blockIdx.y * sPart + c;
     double s = 0.0;
     for (int k = 0; k < chunks; k++) s += p[(int64_t)k * n];
@@ -950,26 +950,76 @@ void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* i
     CUGP_CUDA(cudaGetLastError());
 }
 
-size_t trsv_backward_scratch(int n, int batch) { return (size_t)BWD_PCHUNKS * n * batch; }
+// two partial-sum buffers: the look-ahead sweep runs the near (U1) and far (U2) panel updates concurrently
+size_t trsv_backward_scratch(int n, int batch) { return (size_t)2 * BWD_PCHUNKS * n * batch; }
 
+int trsv_backward_events(int n) { return 2 * cdiv(n, BWD_PANEL) + 2; }
+
+namespace {
+// work[c_lo:c_hi) -= L[P0:P0+rows, c_lo:c_hi)^T alpha[P0:P0+rows)
+void bwd_panel_update(const double* L, int64_t ld, int64_t sL, int n, int P0, int rows, int c_lo, int c_hi, double* work,
+                      const double* alpha, int64_t sVec, double* scratch, int batch, cudaStream_t st) {
+    if (c_hi <= c_lo) return;
+    const int chunks = cdiv(rows, BWD_PROWS);
+    trsv_bwd_panel_kernel<<<dim3(cdiv(c_hi - c_lo, BWD_PCOLS), chunks, batch), TRSV_THREADS, 0, st>>>(
+        L, ld, sL, P0, rows, c_lo, c_hi, alpha, sVec, scratch, (int64_t)BWD_PCHUNKS * n, n);
+    trsv_bwd_panel_reduce_kernel<<<dim3(cdiv(c_hi - c_lo, 256), batch), 256, 0, st>>>(scratch, (int64_t)BWD_PCHUNKS * n, n,
+                                                                                     chunks, c_lo, c_hi, work, sVec);
+}
+}  // namespace
+
+// Two-level backward sweep with look-ahead.  Panel p = rows [P0, P1) (1024 rows):
+//   steps(p): the chain of 128-row block solves inside the panel (latency bound, one launch per block)
+//   U1(p):    the panel's update of the NEXT panel's columns [P0-1024, P0)      -- on the chain's stream
+//   U2(p):    its update of everything left of that, [0, P0-1024): the bulk of the HBM traffic -- stays on `st`,
+//             concurrent with steps(p-1).
+// work[c] receives its updates in the same order as in the single-stream sweep (U2(p+1) before U1(p), U2's in
+// panel order), so the result does not depend on the overlap.  st_chain == nullptr: everything on `st`.
 void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd, double* work,
-                          double* alpha, int64_t sVec, double* scratch, int batch, cudaStream_t st) {
-    for (int P1 = n; P1 > 0;) {
+                          double* alpha, int64_t sVec, double* scratch, int batch, cudaStream_t st, cudaStream_t st_chain,
+                          cudaEvent_t* ev, int nev) {
+    const int npanels = cdiv(n, BWD_PANEL);
+    const bool overlap = st_chain != nullptr && npanels >= 3 && nev >= 2 * npanels + 2;
+    double* scratch1 = scratch;                                       // U1 (and the single-stream sweep)
+    double* scratch2 = scratch + (size_t)BWD_PCHUNKS * n * batch;     // U2
+    // the caller's work vector is ready on `st`; with overlap the chain runs on `st_chain` (the high-priority
+    // look-ahead stream) and the bulk updates stay on `st`
+    cudaStream_t chain = overlap ? st_chain : st;
+    cudaStream_t bulk = st;
+    if (overlap) {
+        CUGP_CUDA(cudaEventRecord(ev[2 * npanels], st));
+        CUGP_CUDA(cudaStreamWaitEvent(chain, ev[2 * npanels], 0));
+    }
+    int p = npanels - 1;
+    for (int P1 = n; P1 > 0; p--) {
         const int P0 = ((P1 - 1) / BWD_PANEL) * BWD_PANEL;
         const int last = P0 + ((P1 - P0 - 1) / DB) * DB;
         for (int j0 = last; j0 >= P0; j0 -= DB) {
             const int ctas = j0 > P0 ? cdiv(j0 - P0, BWD_STEP_COLS) : 1;
-            trsv_bwd_step_kernel<<<dim3(ctas, batch), TRSV_THREADS, 0, st>>>(L, ld, sL, n, j0, P0, invd, sInvd, work, alpha,
-                                                                            sVec);
+            trsv_bwd_step_kernel<<<dim3(ctas, batch), TRSV_THREADS, 0, chain>>>(L, ld, sL, n, j0, P0, invd, sInvd, work, alpha,
+                                                                               sVec);
         }
         if (P0 > 0) {
-            const int chunks = cdiv(P1 - P0, BWD_PROWS);
-            trsv_bwd_panel_kernel<<<dim3(cdiv(P0, BWD_PCOLS), chunks, batch), TRSV_THREADS, 0, st>>>(
-                L, ld, sL, P0, P1 - P0, alpha, sVec, scratch, (int64_t)BWD_PCHUNKS * n, n);
-            trsv_bwd_panel_reduce_kernel<<<dim3(cdiv(P0, 256), batch), 256, 0, st>>>(scratch, (int64_t)BWD_PCHUNKS * n, n, chunks,
-                                                                                    P0, work, sVec);
+            if (!overlap) {
+                bwd_panel_update(L, ld, sL, n, P0, P1 - P0, 0, P0, work, alpha, sVec, scratch1, batch, st);
+            } else {
+                const int Pm = P0 - BWD_PANEL;                      // P0 is a multiple of the panel height
+                CUGP_CUDA(cudaEventRecord(ev[2 * p], chain));       // alpha[P0:P1) is final
+                if (Pm > 0) {
+                    CUGP_CUDA(cudaStreamWaitEvent(bulk, ev[2 * p], 0));
+                    bwd_panel_update(L, ld, sL, n, P0, P1 - P0, 0, Pm, work, alpha, sVec, scratch2, batch, bulk);   // U2(p)
+                    CUGP_CUDA(cudaEventRecord(ev[2 * p + 1], bulk));
+                }
+                // U1(p) writes columns U2(p+1) also wrote (and U2(p+1) exists because P0 > 0): keep that order
+                if (p + 1 < npanels) CUGP_CUDA(cudaStreamWaitEvent(chain, ev[2 * (p + 1) + 1], 0));
+                bwd_panel_update(L, ld, sL, n, P0, P1 - P0, Pm, P0, work, alpha, sVec, scratch1, batch, chain);     // U1(p)
+            }
         }
         P1 = P0;
+    }
+    if (overlap) {
+        CUGP_CUDA(cudaEventRecord(ev[2 * npanels + 1], chain));
+        CUGP_CUDA(cudaStreamWaitEvent(st, ev[2 * npanels + 1], 0));
     }
     CUGP_CUDA(cudaGetLastError());
 }

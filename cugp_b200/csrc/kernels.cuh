@@ -50,9 +50,13 @@ void debug_diag_phases(double* A, int64_t ld, int n, double* invd, double* logde
 // ---- K3: alpha = L^-T z.  (The forward substitution is fused into the Cholesky, gp.cu.)
 // Blocked backward sweep L^T alpha = z (matrixops.cpp:156-164) with the stored inverses of the diagonal blocks;
 // two-level: 128-row block steps inside 1024-row panels, one full-width streaming launch per panel.  `work` holds z
-// on entry and is consumed.
+// on entry and is consumed.  With a second stream `st_chain` and 2 * ceil(n/1024) + 2 events the latency-bound chain
+// of block steps runs there while `st` streams the far part of every panel update (look-ahead of one panel); the
+// result is bit-identical either way.  On return all work is ordered before later work on `st`.
 void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const double* invd, int64_t sInvd,
-                          double* work, double* alpha, int64_t sVec, double* scratch, int batch, cudaStream_t st);
+                          double* work, double* alpha, int64_t sVec, double* scratch, int batch, cudaStream_t st,
+                          cudaStream_t st_chain = nullptr, cudaEvent_t* ev = nullptr, int nev = 0);
+int trsv_backward_events(int n);                 // events the overlapped sweep needs
 size_t trsv_backward_scratch(int n, int batch);  // doubles needed in `scratch`
 // alpha = T^T z with T = L^-1 lower triangular: one streaming pass (used whenever T exists)
 void launch_gemv_t(const double* T, int64_t ld, int64_t sT, int n, const double* z, int64_t sZ, double* alpha,

@@ -51,7 +51,8 @@ long cugp_launch_count(void);
 void cugp_launch_count_reset(void);
 
 /* Tuning knobs (tests and benchmarks).  "potrf_nb": outer block width of the two-level blocked Cholesky, a multiple
- * of 128, 0 = choose by matrix size; "lookahead": 1/0 panel look-ahead on a second stream. */
+ * of 128, 0 = choose by matrix size; "lookahead": 1/0 panel look-ahead on a second stream; "gemm_tpc": consecutive
+ * output tiles one CTA of the DMMA GEMM walks (0 = by grid size). */
 int cugp_set_tuning(const char *key, long value);
 
 /* ---- Covsum (cpp_serial_gp/covkernel.h:3-38) ------------------------------------------------------ */
@@ -159,6 +160,40 @@ int cugp_poe_finalize_dev(const double *PQ_dev, int m, double *mean, double *var
 int cugp_poe_finalize(const double *PQ, int m, double *mean, double *var);
 /* world == 1 convenience: the whole of BCM::compute_BCM_test_means_and_var */
 int cugp_bcm_predict(cugp_bcm *h, const double *Xtest, int m, double *mean, double *var);
+
+/* ---- shard streaming (cuda_scalingdist/cg_solver.cpp:42-70, main.cpp:94-125) -------------------------- */
+/* An expert ensemble whose shards do NOT stay on the GPU: shard i of `numchunks` holds `numtrain` rows of `dim`
+ * values; this rank owns shards rank, rank + world, ... (cg_solver.cpp:44) and evaluates them in groups of `slots`
+ * experts per launch (0 = sized from free device memory).  A reader thread fills two pinned host buffers, a copy
+ * stream uploads group g+1 while group g is being evaluated; one exact GP per shard, sums as in BCM.cpp:153-198.
+ *   _open_files : shard i is <input_prefix><i>.txt ("n d" header, then rows; cuda_gp.cu:477-511) and
+ *                 <label_prefix><i>.txt (one value per line), the reference's argv[7], argv[8] convention
+ *                 (main.cpp:247-252).  Parsed text is kept in host memory up to `host_cache_bytes` (0 = re-parse on
+ *                 every pass, which is what the reference does).
+ *   _open_memory: shards are consecutive numtrain-row blocks of the caller's X, y (kept by pointer, not copied). */
+typedef struct cugp_shardstream cugp_shardstream;
+typedef struct cugp_shardstream_stats {
+    long passes, groups, shards_parsed, cache_hits;
+    double parse_ms;        /* reader thread: text -> double */
+    double reader_wait_ms;  /* main thread blocked on the reader (0 when the parse hides behind the GPU) */
+    double h2d_bytes, cache_bytes;
+} cugp_shardstream_stats;
+int cugp_shardstream_open_files(const char *input_prefix, const char *label_prefix, int numchunks, int numtrain, int dim,
+                                int rank, int world, int slots, size_t host_cache_bytes, cugp_shardstream **out);
+int cugp_shardstream_open_memory(const double *X, const double *y, int numchunks, int numtrain, int dim, int rank,
+                                 int world, int slots, cugp_shardstream **out);
+int cugp_shardstream_close(cugp_shardstream *h);
+int cugp_shardstream_set_loghyper(cugp_shardstream *h, const double theta[3]);
+int cugp_shardstream_get_loghyper(cugp_shardstream *h, double theta[3]);
+int cugp_shardstream_layout(cugp_shardstream *h, int *local_shards, int *slots, int *groups); /* any may be NULL */
+/* compute_log_likelihood_multinode / compute_gradient_log_hyperparams_multinode, cg_solver.cpp:72-131,133-196: one
+ * pass over THIS rank's shards; out4 = (sum LL, sum g0, g1, g2), the caller sums over ranks (allreduce of 4 doubles).
+ * ll_per_shard (may be NULL) receives the local shards' log-likelihoods in shard order. */
+int cugp_shardstream_loglik_grad_local(cugp_shardstream *h, int want_grad, double out4[4], double *ll_per_shard);
+/* product-of-experts moments over this rank's shards, as cugp_bcm_predict_moments[_dev] */
+int cugp_shardstream_predict_moments_dev(cugp_shardstream *h, const double *Xtest, int m, double *PQ_dev);
+int cugp_shardstream_predict_moments(cugp_shardstream *h, const double *Xtest, int m, double *PQ);
+int cugp_shardstream_get_stats(cugp_shardstream *h, cugp_shardstream_stats *out);
 
 /* ---- measurement helpers (bench.py) ----------------------------------------------------------------- */
 /* Sustained FP64 DMMA (mma.sync.m8n8k4.f64) and DFMA throughput of this GPU in TFLOP/s, register resident,
