@@ -284,6 +284,54 @@ def extra_c4(cg, torch, dist, flush, m=10000, reps=4):
             "c4_test_points": m}
 
 
+def extra_f3(cg, torch, dist, flush, chunks=32, n=2000, d=7, slots=8, passes=3):
+    """Shard streaming on the shape of the reference's scaling harness (d = 7 'flight' shards,
+    cuda_scalingdist/harness.sh:53-57; here 32 x 2000 synthetic rows): shard TEXT files -> reader thread -> pinned double
+    buffers -> copy stream -> `slots` experts per launch.  Pass 1 parses the text, later passes hit the host cache; the
+    reported rate is the median cached pass, reader_wait_ms says how much of the parse was NOT hidden behind the GPU."""
+    import shutil
+    import tempfile
+    from cugp_b200.loaders import synthetic_sine
+    rank = dist.get_rank() if dist is not None else 0
+    tmp = os.path.join(tempfile.gettempdir(), "cugp_f3_shards")
+    if rank == 0:
+        shutil.rmtree(tmp, ignore_errors=True)
+        os.makedirs(tmp)
+        X, y = synthetic_sine(chunks * n, d, seed=3)
+        for i in range(chunks):
+            np.savetxt(os.path.join(tmp, f"in_{i}.txt"), X[i * n:(i + 1) * n], fmt="%.17g", header=f"{n} {d}", comments="")
+            np.savetxt(os.path.join(tmp, f"lab_{i}.txt"), y[i * n:(i + 1) * n], fmt="%.17g")
+    if dist is not None:
+        dist.barrier()
+    s = cg.ShardStream.from_files(os.path.join(tmp, "in_"), os.path.join(tmp, "lab_"), chunks, n, d, slots=slots)
+    ts = []
+    for i in range(passes + 1):
+        s.set_BCM_log_hyperparam([TH_C[0] + 1e-7 * i, TH_C[1], TH_C[2]])
+        flush()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        s.loglik_and_gradient()
+        ts.append(time.perf_counter() - t)
+    st, lay = s.stats(), s.layout()
+    s.close()
+    v = statistics.median(ts[1:])
+    if dist is not None:
+        tt = torch.tensor([v, ts[0]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        v, first = float(tt[0].item()), float(tt[1].item())
+        dist.barrier()
+    else:
+        first = ts[0]
+    if rank == 0:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"f3_stream_shape": f"{chunks} shards x {n} rows x d={d}, {lay['slots']} slots, {lay['groups']} groups/pass on rank 0",
+            "f3_stream_loglik_grad_evals_per_s": 1.0 / v, "f3_first_pass_s_incl_text_parse": first,
+            "f3_parse_ms_rank0": st["parse_ms"], "f3_reader_wait_ms_rank0": st["reader_wait_ms"],
+            "f3_h2d_bytes_per_pass_rank0": st["h2d_bytes"] / max(st["passes"], 1)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -294,6 +342,7 @@ def main():
     ap.add_argument("--m", type=int, default=10000, help="test points (c3/c4)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (scaling sweeps: it is rank-0 only work)")
     a = ap.parse_args()
     a.n = a.n or {"c5": 100000, "c3": 10000, "c2": 4096, "c4": 24000}[a.workload]
     a.warmup = max(a.warmup, 3) if a.impl == "native" else a.warmup
@@ -470,10 +519,21 @@ def main():
             extra = dict(extra or {}, c2_loglik_grad_evals_per_s=extra_c2(cg, torch, flush))
         except Exception as e:
             extra = dict(extra or {}, c2_error=repr(e))
+        try:
+            extra.update(extra_f3(cg, torch, dist, flush))   # collective: shards i % world == rank, allreduce(4)
+        except Exception as e:
+            extra["f3_error"] = repr(e)
         out["extra"] = extra
     n_s = 2048 if a.workload in ("c5", "c3") else 1024
-    cpu = cpu_baseline("reference", n_s, TH_B)
-    if a.workload == "c2":
+    skip_cpu = a.no_cpu or world != 1          # the CPU baseline is a rank-0, N = 1 leg
+    if skip_cpu:
+        cpu = {"value": None, "unit": None, "cores": 0, "kind": "skipped",
+               "sample": "--no-cpu" if a.no_cpu else "reported at N=1 only"}
+    elif a.workload in ("c5", "c3"):
+        cpu = cpu_baseline("reference", n_s, TH_B)
+    if skip_cpu:
+        pass
+    elif a.workload == "c2":
         from oracle import oracle
         impl = oracle.reference() or oracle.port()
         Xs, ys = synthetic_sine(n_s, 10, lo=-20.0, hi=20.0, noise=0.05)
@@ -484,8 +544,17 @@ def main():
         cpu = {"value": 1.0 / dt, "unit": "evals/s", "cores": 1, "kind": impl.kind,
                "sample": f"one LL + gradient at n={n_s} (of {n}), theta_B, {dt:.1f} s"}
     elif a.workload == "c4":
-        cpu = {"value": None, "unit": "pts/s", "cores": 1, "kind": "reference",
-               "sample": "see BASELINE.md: BCM 16x1500 predict(8 pts) 172 s on one core"}
+        # bounded sample: ONE of the 16 experts (its factorisation, inverse and 8 predictions are 1/16 of the ensemble's
+        # sequential CPU work, BCM.cpp:64-83), scaled to the ensemble
+        from oracle import oracle
+        impl = oracle.reference() or oracle.port()
+        d4 = np.load(os.path.join(ROOT, "tests", "golden", "data_si24000.npz"))
+        m_s = 8
+        t = time.perf_counter()
+        impl.predict(d4["X"][:1500], d4["y"][:1500], TH_C, d4["Xtest"][:m_s])
+        dt = time.perf_counter() - t
+        cpu = {"value": m_s / (16.0 * dt), "unit": "pts/s", "cores": 1, "kind": impl.kind,
+               "sample": f"expert 0 of 16 (1500 rows): train + predict {m_s} points, theta_C, {dt:.1f} s; ensemble = 16 x that"}
     line = {"metric": out.pop("metric"), "value": out.pop("value"), "unit": out.pop("unit"), "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": out.pop("ms_per_step"), "higher_is_better": True, "scaling": out.pop("scaling"),
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,

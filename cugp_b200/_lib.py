@@ -90,6 +90,7 @@ SIGNATURES = {
     "cugp_shardstream_loglik_grad_local": (C.c_int, [C.c_void_p, C.c_int, dp, dp]),
     "cugp_shardstream_predict_moments_dev": (C.c_int, [C.c_void_p, dp, C.c_int, C.c_void_p]),
     "cugp_shardstream_predict_moments": (C.c_int, [C.c_void_p, dp, C.c_int, dp]),
+    "cugp_shardstream_parse_file": (C.c_int, [C.c_char_p, C.c_int, C.c_size_t, dp]),
     "cugp_shardstream_get_stats": (C.c_int, [C.c_void_p, C.POINTER(ShardStreamStats)]),
     "cugp_probe_fp64_peak": (C.c_int, [C.c_float, dp, dp]),
     "cugp_probe_dmma": (C.c_int, [C.c_float, dp, dp]),

@@ -126,12 +126,29 @@ int cugp_set_tuning(const char* key, long value) {
         set_lookahead(value != 0);
         return CUGP_OK;
     }
+    if (std::strcmp(key, "bwd_cluster") == 0) {
+        set_bwd_cluster(value != 0);
+        bump_tuning_epoch();
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "gemm_raster") == 0) {
+        if (value < 0 || value > 256) return CUGP_ERR_INVALID;
+        set_gemm_raster_width((int)value);
+        bump_tuning_epoch();
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "graph_max_n") == 0) {
+        if (value < 0) return CUGP_ERR_INVALID;
+        set_graph_max_n((int)value);
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "gemm_tpc") == 0) {
         if (value < 0 || value > 64) {
             set_last_error("gemm_tpc must be 0 (auto) or 1..64");
             return CUGP_ERR_INVALID;
         }
         set_gemm_tiles_per_cta((int)value);
+        bump_tuning_epoch();
         return CUGP_OK;
     }
     set_last_error("unknown tuning key '%s'", key);
@@ -668,14 +685,25 @@ int cugp_bcm_predict_moments(cugp_bcm* h, const double* Xtest, int m, double* PQ
 int cugp_poe_finalize_dev(const double* PQ_dev, int m, double* mean, double* var) {
     CUGP_TRY
     if (!PQ_dev || m <= 0 || !mean || !var) return CUGP_ERR_INVALID;
-    double* out = nullptr;
-    CUGP_CUDA(cudaMalloc((void**)&out, (size_t)2 * m * 8));
+    // grow-only scratch (device + pinned host): this call sits behind every multi-GPU prediction's allreduce, and a
+    // cudaMalloc/cudaFree pair per call costs more than the kernel and both copies together
+    static double* out = nullptr;
+    static double* hout = nullptr;
+    static int cap = 0;
+    if (m > cap) {
+        if (out) cudaFree(out);
+        if (hout) cudaFreeHost(hout);
+        out = hout = nullptr;
+        cap = 0;
+        CUGP_CUDA(cudaMalloc((void**)&out, (size_t)2 * m * 8));
+        CUGP_CUDA(cudaMallocHost((void**)&hout, (size_t)2 * m * 8));
+        cap = m;
+    }
     launch_poe_finalize(PQ_dev, m, out, out + m, 0);
-    cudaError_t e1 = cudaMemcpy(mean, out, (size_t)m * 8, cudaMemcpyDeviceToHost);
-    cudaError_t e2 = cudaMemcpy(var, out + m, (size_t)m * 8, cudaMemcpyDeviceToHost);
-    cudaFree(out);
-    CUGP_CUDA(e1);
-    CUGP_CUDA(e2);
+    CUGP_CUDA(cudaMemcpyAsync(hout, out, (size_t)2 * m * 8, cudaMemcpyDeviceToHost, 0));
+    CUGP_CUDA(cudaStreamSynchronize(0));
+    std::memcpy(mean, hout, (size_t)m * 8);
+    std::memcpy(var, hout + m, (size_t)m * 8);
     return CUGP_OK;
     CUGP_CATCH
 }

@@ -2,6 +2,8 @@
 // mma.sync.m8n8k4.f64 (DMMA.8x8x4).  No cuBLAS anywhere in the product path.
 #include "gemm_dmma.cuh"
 
+#include <algorithm>
+
 namespace cugp {
 
 namespace {
@@ -34,7 +36,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // ------------------------------------------------------------------------------------------------
 constexpr int WBK = 32;        // k-depth of one stage
 constexpr int WPAD = 4;        // (WBK + WPAD) % 16 == 4 and (ROWS + WPAD) % 16 == 4: conflict-free 8-byte fragments
-constexpr int RASTER_W = 8;    // tile columns per raster strip
+constexpr int RASTER_W_DEFAULT = 8;    // tile columns per raster strip
 
 template <int ROWS, bool KC>
 __host__ __device__ constexpr int ws_tile_doubles() {
@@ -62,7 +64,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 // Linear block index -> output tile.  lower: tiles with ti >= tj of a tm x tn (tm >= tn) trapezoid.
-__device__ __forceinline__ void raster_tile(int x, int tm, int tn, bool lower, int& ti, int& tj) {
+__device__ __forceinline__ void raster_tile(int x, int tm, int tn, bool lower, int RASTER_W, int& ti, int& tj) {
     int s = 0, w, rows;
     if (lower) {
         for (;;) {
@@ -153,7 +155,10 @@ __device__ __forceinline__ TileGeom tile_geom(const GemmParams& p, int64_t t, in
     // consecutive work items walk the raster order of one matrix, then the next batch entry
     g.b = t / p.tiles_per_mat;
     int ti, tj;
-    raster_tile((int)(t - g.b * p.tiles_per_mat), tiles_m, tiles_n, p.lower_tiles != 0, ti, tj);
+    raster_tile((int)(t - g.b * p.tiles_per_mat), tiles_m, tiles_n, p.lower_tiles != 0, p.raster_w, ti, tj);
+    // k < (ti+1)*BM (triangular left operand, e.g. V = T Kstar^T): the k-range grows with ti, so walk the tile rows
+    // from the bottom up -- the longest tiles start first and the short ones fill the tail of the grid
+    if (p.khi_ti && !p.lower_tiles) ti = tiles_m - 1 - ti;
     g.ti = ti;
     g.m0 = ti * BM;
     g.n0 = tj * BN;
@@ -178,12 +183,18 @@ __device__ __forceinline__ TileGeom tile_geom(const GemmParams& p, int64_t t, in
     return g;
 }
 
-// Each CTA owns `tiles_per_cta` consecutive tiles of the raster order and walks them with ONE running stage
-// counter: the producer warp group is never more than NSTAGE stages ahead of the math warps but it does not stop at
-// a tile boundary, so the next tile's first stages (and its C tile, prefetched into L2) are in flight while the
-// math warps run the epilogue of the current one -- the pipeline fill and most of the epilogue latency are paid
-// once per CTA instead of once per tile.  The count stays small (<= 8) so CTAs keep retiring every few hundred
-// microseconds and the high-priority panel stream of the look-ahead Cholesky still finds free SMs.
+// Each CTA walks `tiles_per_cta` tiles with ONE running stage counter: the producer warp group is never more than
+// NSTAGE stages ahead of the math warps but it does not stop at a tile boundary, so the next tile's first stages (and
+// its C tile, prefetched into L2) are in flight while the math warps run the epilogue of the current one -- the
+// pipeline fill and most of the epilogue latency are paid once per CTA instead of once per tile.  The count stays
+// small (<= 8) so CTAs keep retiring every few hundred microseconds and the high-priority panel stream of the
+// look-ahead Cholesky still finds free SMs.
+// Which tiles: the grid is cut into rounds of `cta_stride` (= number of SMs) CTAs; round r covers the
+// cta_stride * tiles_per_cta consecutive tiles of the raster order starting at r * cta_stride * tiles_per_cta, and CTA c
+// of the round takes tiles c, c + cta_stride, c + 2 cta_stride, ...  So the tiles in flight at any moment are
+// ~cta_stride CONSECUTIVE tiles of the raster order, exactly as with one tile per CTA (giving every CTA a run of
+// consecutive tiles instead spread the in-flight set over 4x as many tile rows: 74 MB of operand panels, more than
+// the L2 holds next to the C stream -- DRAM reads of the first K = 1024 update at n = 40 000 went from 12 to 26 GB).
 template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_kernel(const GemmParams p) {
     constexpr int NCW = WARPS_M * WARPS_N;  // consumer warps
@@ -200,8 +211,8 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-    const int64_t t_begin = (int64_t)blockIdx.x * p.tiles_per_cta;
-    const int64_t t_end = min(t_begin + p.tiles_per_cta, p.tiles_per_mat * (int64_t)p.batch);
+    const int64_t t_total = p.tiles_per_mat * (int64_t)p.batch;
+    const int64_t t_base = (int64_t)(blockIdx.x / p.cta_stride) * p.cta_stride * p.tiles_per_cta + blockIdx.x % p.cta_stride;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) {
@@ -220,7 +231,9 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
         if (kRegSplit) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
         const int pl = tid - NCW * 32;  // producer lane
         unsigned it = 0;                // stages issued by this CTA so far (all tiles)
-        for (int64_t t = t_begin; t < t_end; t++) {
+        for (int step = 0; step < p.tiles_per_cta; step++) {
+            const int64_t t = t_base + (int64_t)step * p.cta_stride;
+            if (t >= t_total) break;
             const TileGeom g = tile_geom<BM, BN>(p, t, tiles_m, tiles_n);
             const double* __restrict__ A = p.A + g.offA;
             const double* __restrict__ B = p.B + g.offB;
@@ -252,7 +265,9 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
     const int g = lane >> 2, q = lane & 3;
     const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
     unsigned it = 0;
-    for (int64_t t = t_begin; t < t_end; t++) {
+    for (int step = 0; step < p.tiles_per_cta; step++) {
+        const int64_t t = t_base + (int64_t)step * p.cta_stride;
+        if (t >= t_total) break;
         const TileGeom tg = tile_geom<BM, BN>(p, t, tiles_m, tiles_n);
         const int m0 = tg.m0, n0 = tg.n0;
         double acc[MI][NI][2];
@@ -384,6 +399,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
     }
 }
 
+static int g_raster_w = RASTER_W_DEFAULT;
 static int g_tiles_per_cta = 0;  // 0: by grid size; otherwise forced (cugp_set_tuning("gemm_tpc", v))
 
 template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC>
@@ -414,9 +430,23 @@ void launch_ws(const GemmParams& p_in, cudaStream_t stream) {
     // (measured, profiles/r1_gemm_tpc_sweep.txt: 8192^2 x 1024 probe 34.1 -> 34.6 TFLOP/s, 32768^2 34.6 -> 35.0 at 4 tiles
     // per CTA; the n = 10 000 Cholesky loses 7 % at 2 because its look-ahead panel stream then waits for SMs)
     if (tpc <= 0) tpc = total >= 148 * 512 ? 8 : total >= 148 * 96 ? 4 : total >= 148 * 40 ? 2 : 1;
+    static const int sms = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
     p.tiles_per_mat = tiles;
     p.tiles_per_cta = tpc;
-    dim3 grid((unsigned)((total + tpc - 1) / tpc));
+    p.cta_stride = tpc > 1 ? sms : 1;
+    p.raster_w = g_raster_w;
+    const int64_t per_round = (int64_t)p.cta_stride * tpc;   // tiles one round of cta_stride CTAs covers
+    const int64_t rounds = (total + per_round - 1) / per_round;
+    int64_t ctas = rounds * p.cta_stride;
+    if (tpc > 1) {   // drop the CTAs of the last round that have no first tile
+        const int64_t last_base = (rounds - 1) * per_round;
+        ctas = (rounds - 1) * p.cta_stride + std::min<int64_t>(p.cta_stride, total - last_base);
+    }
+    dim3 grid((unsigned)ctas);
     kern<<<grid, NT, smem, stream>>>(p);
     CUGP_CUDA(cudaGetLastError());
 }
@@ -432,6 +462,7 @@ void launch_layout(const GemmParams& p, bool a_kc, bool b_kc, cudaStream_t strea
 }  // namespace
 
 void set_gemm_tiles_per_cta(int v) { g_tiles_per_cta = v; }
+void set_gemm_raster_width(int v) { g_raster_w = v > 0 ? v : RASTER_W_DEFAULT; }
 
 int gemm_tile_m(GemmConfig cfg) { return cfg == GEMM_BIG ? 128 : 64; }
 

@@ -32,7 +32,9 @@ struct GemmParams {
     double* colsumsq;        // non-null: write per-row-tile column sums of squares [tiles_m][N] instead of C
     int64_t sCss;            // batch stride of colsumsq
     int64_t tiles_per_mat;   // filled by the launcher: output tiles of one matrix (raster order)
-    int tiles_per_cta;       // filled by the launcher: consecutive work items (tile, batch) one CTA walks
+    int tiles_per_cta;       // filled by the launcher: work items (tile, batch) one CTA walks
+    int cta_stride;          // filled by the launcher: distance between a CTA's successive tiles (SM count; 1 if tpc == 1)
+    int raster_w;            // filled by the launcher: tile columns per raster strip
 };
 
 enum GemmConfig { GEMM_BIG = 0, GEMM_TALL = 1, GEMM_SMALL = 2 };
@@ -44,5 +46,6 @@ GemmConfig pick_config(int M, int N, int batch, bool lower_tiles);
 int gemm_tile_m(GemmConfig cfg);
 // Tuning: tiles walked per CTA (0 = by grid size).
 void set_gemm_tiles_per_cta(int v);
+void set_gemm_raster_width(int v);   // tile columns per raster strip (0 = default)
 
 }  // namespace cugp

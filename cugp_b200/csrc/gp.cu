@@ -39,11 +39,19 @@ static cudaEvent_t prof_event(GpBatch::Prof* prof) {
 // Outer block width of the two-level factorisation: the trailing update runs with K = outer width, so its
 // C tiles are read and written once per outer step instead of once per 128 columns (the K = 128 update is
 // bound by that traffic: 8 flop/B).  Small matrices keep narrow outer blocks so the update still fills the GPU.
+static long g_epoch = 0;
+long tuning_epoch() { return g_epoch; }
+void bump_tuning_epoch() { g_epoch++; }
+// measured (profiles/r1_graph_replay.txt): n = 1500 LL+grad 1.28 -> 1.18 ms, but 4.50 -> 4.80 ms at n = 4096 and
+// 36.1 -> 37.4 ms at n = 10 000 -- once the bulk updates matter, graph branches lose the stream-priority scheduling
+// the look-ahead relies on
+static int g_graph_max_n = 2048;
+void set_graph_max_n(int n) { g_graph_max_n = n; bump_tuning_epoch(); }
 static int g_lookahead = 1;
-void set_lookahead(int v) { g_lookahead = v; }
+void set_lookahead(int v) { g_lookahead = v; bump_tuning_epoch(); }
 bool lookahead_enabled() { return g_lookahead != 0; }
 static int g_potrf_nb = 0;  // 0: by size; otherwise forced (cugp_set_tuning("potrf_nb", v) or CUGP_POTRF_NB)
-void set_potrf_outer_width(int nb) { g_potrf_nb = nb; }
+void set_potrf_outer_width(int nb) { g_potrf_nb = nb; bump_tuning_epoch(); }
 int potrf_outer_width(int n) {
     static const int env = [] {
         const char* e = std::getenv("CUGP_POTRF_NB");
@@ -265,6 +273,9 @@ GpBatch::~GpBatch() {
     for (cudaEvent_t e : prof.ev) cudaEventDestroy(e);
     for (cudaEvent_t e : la.ev) cudaEventDestroy(e);
     for (cudaEvent_t e : bwd_ev) cudaEventDestroy(e);
+    for (auto* cache : {&graph_potrf, &graph_potrf_rhs, &graph_inv})
+        for (auto& kv : *cache)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (la.st2) {
         cudaStreamSynchronize(la.st2);
         cudaStreamDestroy(la.st2);
@@ -349,24 +360,73 @@ void GpBatch::set_theta(const double th[3]) {
     invalidate();
 }
 
+// Replay `body` (a fixed sequence of launches on `st` and the look-ahead stream, independent of theta) as a CUDA graph.
+// First use: direct run (kernel attributes get configured, events created).  Second use: stream capture, instantiate,
+// launch.  Later: launch.  A failed capture disables the graph for this batch and the caller launches directly.
+template <class F>
+bool GpBatch::run_graphed(std::map<int, GraphEntry>& cache, F&& body) {
+    if (n > g_graph_max_n || prof.on) return false;
+    GraphEntry& e = cache[B];
+    if (e.failed) return false;
+    if (e.exec && e.epoch != tuning_epoch()) {
+        cudaGraphExecDestroy(e.exec);
+        e.exec = nullptr;
+        e.uses = 0;
+    }
+    if (!e.exec) {
+        if (e.uses++ == 0) return false;
+        const long before = launches;
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            try {
+                body();
+            } catch (const CudaError&) {
+                ok = false;
+            }
+            ok = (cudaStreamEndCapture(st, &graph) == cudaSuccess) && ok && graph != nullptr;
+        }
+        e.launches = launches - before;
+        launches = before;
+        if (ok) ok = cudaGraphInstantiate(&e.exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) {
+            cudaGetLastError();
+            e.exec = nullptr;
+            e.failed = true;
+            return false;
+        }
+        e.epoch = tuning_epoch();
+    }
+    CUGP_CUDA(cudaGraphLaunch(e.exec, st));
+    launches += e.launches;
+    return true;
+}
+
 void GpBatch::build_K(int full) {
     launch_cov_train(X, (int64_t)n * dp, n, dp, h, Kb, ld, mat_stride(), B, full, st);
     launches++;
 }
 
 void GpBatch::potrf(bool with_rhs) {
-    potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la,
-                  with_rhs ? 1 : 0);
+    auto body = [&] {
+        potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la,
+                      with_rhs ? 1 : 0);
+    };
+    if (with_rhs || !run_graphed(graph_potrf, body)) body();   // graph_potrf holds the rhs-free sequence only
 }
 
 // Cholesky of the matrix in Kb with y appended as row n: L in place, z = L^-1 y in row n, then
 // (quad = z'z = y'K^-1 y, logdet, LL) -- matrixops.cpp:113-185 + covkernel.cpp:127 without a separate forward sweep.
 void GpBatch::potrf_with_rhs() {
-    launch_copy_rows(y, n, Kb + (int64_t)n * ld, mat_stride(), n, B, st);
-    potrf(true);
-    const double* zrow = Kb + (int64_t)n * ld;
-    launch_ll_finalize(zrow, zrow, mat_stride(), n, logdet_part, nblk, scal, B, st);
-    launches += 2;
+    auto body = [&] {
+        launch_copy_rows(y, n, Kb + (int64_t)n * ld, mat_stride(), n, B, st);
+        potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la, 1);
+        const double* zrow = Kb + (int64_t)n * ld;
+        launch_ll_finalize(zrow, zrow, mat_stride(), n, logdet_part, nblk, scal, B, st);
+        launches += 2;
+    };
+    if (!run_graphed(graph_potrf_rhs, body)) body();
 }
 
 void GpBatch::prof_begin() {
@@ -402,8 +462,8 @@ void GpBatch::solve() {
     factorize();
     const double* zrow = Kb + (int64_t)n * ld;
     if (have_T) {
-        launch_gemv_t(Tb, ld, mat_stride(), n, zrow, mat_stride(), alpha, n, B, st);
-        launches += 1;
+        launch_gemv_t(Tb, ld, mat_stride(), n, zrow, mat_stride(), alpha, n, tpart, B, st);
+        launches += 2;
     } else {
         const int64_t sI = (int64_t)nblk * kDiag * kDiag;
         launch_copy_rows(zrow, mat_stride(), work, n, n, B, st);  // the sweep consumes its right-hand side
@@ -415,7 +475,7 @@ void GpBatch::solve() {
         }
         launch_trsv_backward(Kb, ld, mat_stride(), n, invd, sI, work, alpha, n, tpart, B, st,
                              lookahead_enabled() ? la.st2 : nullptr, bwd_ev.data(), nev);
-        launches += 1 + nblk + 2 * (cdiv(n, 1024) - 1);
+        launches += 1 + 3 * cdiv(n, 1024);  // per panel: chain, near update, far update
     }
     have_alpha = true;
 }
@@ -464,7 +524,19 @@ void GpBatch::loglik(double* ll_out) {
 }
 
 void GpBatch::gradient_launch() {
-    trtri();   // before solve(): alpha then is a single pass over T
+    factorize();
+    if (!have_T && !have_alpha && !have_Kinv) {
+        // the whole inverse chain (TRTRI recursion, alpha = T^T z, LAUUM) is theta independent: one graph replay
+        ensure_TW();
+        auto body = [&] {
+            have_T = have_alpha = have_Kinv = false;
+            trtri();   // before solve(): alpha then is a single pass over T
+            solve();
+            lauum();
+        };
+        if (run_graphed(graph_inv, body)) have_T = have_alpha = have_Kinv = true;
+    }
+    trtri();
     solve();
     lauum();
     dalloc(gradpart, grad_trace_partials(n, Bcap));

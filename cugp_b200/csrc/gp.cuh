@@ -7,6 +7,7 @@
 #include "gemm_dmma.cuh"
 #include "kernels.cuh"
 
+#include <map>
 #include <vector>
 
 namespace cugp {
@@ -57,6 +58,18 @@ struct GpBatch {
     } prof;
     PotrfLookahead la;
     std::vector<cudaEvent_t> bwd_ev;       // events of the overlapped backward sweep
+    // CUDA graphs of the theta-independent launch chains (small and medium n are bound by the chain of dependent
+    // launches across two streams, not by any kernel): captured on the second use, keyed by the active batch count.
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        long launches = 0;   // kernels one replay launches
+        long epoch = -1;     // tuning epoch at capture
+        int uses = 0;        // direct runs before the capture (the first one configures kernel attributes, creates events)
+        bool failed = false;
+    };
+    std::map<int, GraphEntry> graph_potrf, graph_potrf_rhs, graph_inv;
+    template <class F>
+    bool run_graphed(std::map<int, GraphEntry>& cache, F&& body);   // false: caller runs `body` directly
     void prof_begin();                     // reset counters (events are reused)
     void prof_collect(double* ms, double* flops, long* count);
 
@@ -104,6 +117,11 @@ struct GpBatch {
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part,
                    int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr, PotrfLookahead* la = nullptr,
                    int rhs_rows = 0);
+// Tuning epoch: bumped by every tuning change so cached graphs are re-captured.  graph_max_n: largest n whose launch
+// chains are replayed as CUDA graphs (0 disables).
+long tuning_epoch();
+void bump_tuning_epoch();
+void set_graph_max_n(int n);
 void set_lookahead(int v);  // 1 (default): factor panel J+1 on a second stream while panel J's trailing update runs
 bool lookahead_enabled();
 // Outer block width used for an n x n factorisation; set_potrf_outer_width(0) restores the size-based default.

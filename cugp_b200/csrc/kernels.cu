@@ -7,6 +7,8 @@
 // Every reduction is a fixed-shape tree over per-CTA partials: results are run-to-run deterministic.
 #include "kernels.cuh"
 
+#include <cooperative_groups.h>
+
 namespace cugp {
 
 namespace {
@@ -664,99 +666,219 @@ __global__ void __launch_bounds__(TRSV_THREADS)
     }
 }
 
-// Outer step of the two-level backward sweep: all columns left of a finished panel of rows [P0, P0 + rows) receive
-// s[c] -= sum_r L[P0+r][c] alpha[P0+r].  The rows x P0 slab of L is streamed once at full width by a 2-D grid
-// (128 columns x 128 rows per CTA, 32 independent 16-byte loads per thread); the row chunks leave partial sums
-// that a second small kernel adds in a fixed order (deterministic, no atomics).  The per-128-row launches
-// inside the panel only touch the panel's own columns and stay in L2.
-constexpr int BWD_PANEL = 1024;
-constexpr int BWD_PCOLS = 128, BWD_PROWS = 128, BWD_PCHUNKS = BWD_PANEL / BWD_PROWS;
-__global__ void __launch_bounds__(TRSV_THREADS)
-    trsv_bwd_panel_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int P0, int rows, int c_lo, int c_hi,
-                          const double* __restrict__ alpha, int64_t sVec, double* partial, int64_t sPart, int n) {
-    __shared__ double ap[BWD_PROWS];
-    __shared__ double red[4][BWD_PCOLS];
+// The whole chain of one 1024-row panel in ONE launch: a thread-block cluster of up to 8 CTAs, CTA c owning the
+// panel's c-th block of 128 columns -- its slice s_c of the right-hand side and the inverse of its diagonal block
+// live in that CTA's shared memory for the whole launch.  Step j (from the bottom block up):
+//   CTA j:    alpha_j = inv(L_jj)^T s_j      (128x128 mat-vec out of shared memory)
+//             -> global alpha, and into the landing buffer of every CTA c < j through distributed shared memory
+//   cluster barrier (release/acquire)
+//   CTA c<j:  s_c -= L[block j, block c]^T alpha_j, from registers: the 128x128 block of L was requested one step
+//             earlier, before the barrier wait (its address does not depend on alpha), so the HBM/L2 round trip of
+//             every step overlaps the previous step's dependent work.
+// This replaces 8 dependent launches (each a chain of global round trips: right-hand side, inverse block, L block,
+// write-back) by one; the per-step cost becomes a shared-memory mat-vec plus one cluster barrier.
+namespace cgs = cooperative_groups;
+constexpr int PC_THREADS = 512;
+constexpr size_t PC_SMEM = (size_t)(DB * DB + DB + 2 * DB + 8 * DB) * sizeof(double);
+
+__global__ void __launch_bounds__(PC_THREADS, 1)
+    trsv_bwd_chain_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int n, int P0, int nbk,
+                          const double* __restrict__ invd, int64_t sInvd, const double* __restrict__ work, double* alpha,
+                          int64_t sVec) {
+    cgs::cluster_group cluster = cgs::this_cluster();
+    extern __shared__ __align__(16) double pcs[];
+    double* inv = pcs;                  // [128][128] inverse of this CTA's diagonal block (zero upper triangle)
+    double* s = inv + DB * DB;          // [128] this CTA's slice of the right-hand side
+    double* abuf = s + DB;              // [2][128] landing buffers for alpha_j (alternating by step parity)
+    double* part = abuf + 2 * DB;       // [8][128] partial sums
     const int tid = threadIdx.x;
-    const int64_t b = blockIdx.z;
+    const int c = (int)cluster.block_rank();   // == blockIdx.x: grid.x equals the cluster width
+    const int64_t b = blockIdx.y;
+    L += b * sL;
+    work += b * sVec;
+    alpha += b * sVec;
+    const int jc = P0 + c * DB;                // first row / column of this CTA's block
+    const int nbc = min(DB, n - jc);
+    {
+        const double2* src = reinterpret_cast<const double2*>(invd + b * sInvd + (int64_t)(jc / DB) * DB * DB);
+        double2 v[DB * DB / 2 / PC_THREADS];
+#pragma unroll
+        for (int i = 0; i < DB * DB / 2 / PC_THREADS; i++) v[i] = src[tid + PC_THREADS * i];
+#pragma unroll
+        for (int i = 0; i < DB * DB / 2 / PC_THREADS; i++) reinterpret_cast<double2*>(inv)[tid + PC_THREADS * i] = v[i];
+        if (tid < DB) s[tid] = tid < nbc ? work[jc + tid] : 0.0;
+    }
+    // thread (column pair cp, row group rg): 16 rows x 2 columns of the 128x128 block of L below this CTA's block
+    const int cp = tid & 63, rg = tid >> 6;
+    double2 lv[16];
+    auto request = [&](int j) {   // block (j, c): rows P0 + 128 j + ..., columns jc + ...
+        const int r0 = P0 + j * DB + rg * 16;
+        const double* src = L + (int64_t)r0 * ld + jc + 2 * cp;
+#pragma unroll
+        for (int u = 0; u < 16; u++)
+            lv[u] = (r0 + u < n) ? *reinterpret_cast<const double2*>(src + (int64_t)u * ld) : make_double2(0.0, 0.0);
+    };
+    if (c < nbk - 1) request(nbk - 1);
+    cluster.sync();   // every CTA's shared memory is initialised before the first remote store
+    for (int j = nbk - 1; j >= 0; j--) {
+        double* ab = abuf + (j & 1) * DB;
+        if (c == j) {
+            // alpha_j[col] = sum_r inv[r][col] s[r]: thread (col, q) takes rows q, q+4, ...
+            const int col = tid & (DB - 1), q = tid >> 7;
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+            for (int r = q; r < DB; r += 8) {
+                a0 += inv[r * DB + col] * s[r];
+                a1 += inv[(r + 4) * DB + col] * s[r + 4];
+            }
+            part[q * DB + col] = a0 + a1;
+            __syncthreads();
+            if (tid < DB) {
+                const double a = (part[tid] + part[DB + tid]) + (part[2 * DB + tid] + part[3 * DB + tid]);
+                if (tid < nbc) alpha[jc + tid] = a;
+                for (int dst = 0; dst < j; dst++) cluster.map_shared_rank(ab, dst)[tid] = a;
+            }
+        }
+        cluster.sync();
+        if (c < j) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const double av = ab[rg * 16 + u];
+                a0 += lv[u].x * av;
+                a1 += lv[u].y * av;
+            }
+            if (j - 1 > c) request(j - 1);   // next step's block: in flight across the next barrier
+            part[rg * DB + 2 * cp] = a0;
+            part[rg * DB + 2 * cp + 1] = a1;
+            __syncthreads();
+            if (tid < DB) {
+                double t = 0.0;
+#pragma unroll
+                for (int g = 0; g < 8; g++) t += part[g * DB + tid];
+                s[tid] -= t;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Outer step of the two-level backward sweep: the columns [c_lo, c_hi) left of a finished panel of rows
+// [P0, P0 + rows) receive s[c] -= sum_r L[P0+r][c] alpha[P0+r].  One CTA owns 64 columns for ALL rows of the panel
+// (up to 8 sub-blocks of 128 rows, 16 independent 16-byte loads per thread each, two CTAs per SM), so every column
+// is reduced by exactly one CTA in a fixed order and written once: no partial sums, no second kernel, no atomics.
+// (A 2-D grid with per-chunk partials and a reduction launch streamed the slab at 4.7 TB/s; the extra launch
+// boundary per panel drained the GPU twice as often.)  The per-128-row steps inside the panel only touch the panel's
+// own columns and stay in L2.
+constexpr int BWD_PANEL = 1024;
+constexpr int BWD_PCHUNKS = BWD_PANEL / DB;
+constexpr int BWD_UCOLS = 64;
+__global__ void __launch_bounds__(TRSV_THREADS, 2)
+    trsv_bwd_update_kernel(const double* __restrict__ L, int64_t ld, int64_t sL, int P0, int rows, int c_lo, int c_hi,
+                           const double* __restrict__ alpha, double* work, int64_t sVec) {
+    __shared__ double ap[BWD_PANEL];
+    __shared__ double red[8][BWD_UCOLS];
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.y;
     L += b * sL;
     alpha += b * sVec;
-    partial += b * sPart + (int64_t)blockIdx.y * n;
-    const int r0 = blockIdx.y * BWD_PROWS;                 // first row of this chunk inside the panel
-    if (tid < BWD_PROWS) ap[tid] = (r0 + tid < rows) ? alpha[P0 + r0 + tid] : 0.0;
-    const int cp = tid & 63, rg = tid >> 6;                // column pair, row group (32 rows each)
-    const int c = c_lo + blockIdx.x * BWD_PCOLS + cp * 2;   // c_lo, c_hi even: a column pair never straddles c_hi
-    double a0 = 0.0, a1 = 0.0;
-    double2 v[32];
-    if (c < c_hi) {
-        const double* src = L + (int64_t)(P0 + r0 + rg * 32) * ld + c;
-#pragma unroll
-        for (int u = 0; u < 32; u++)
-            v[u] = (r0 + rg * 32 + u < rows) ? *reinterpret_cast<const double2*>(src + (int64_t)u * ld) : make_double2(0.0, 0.0);
-    }
+    work += b * sVec;
+    for (int i = tid; i < BWD_PANEL; i += TRSV_THREADS) ap[i] = i < rows ? alpha[P0 + i] : 0.0;
+    const int cp = tid & 31, rg = tid >> 5;                // column pair, row group (16 rows of every 128)
+    const int c = c_lo + blockIdx.x * BWD_UCOLS + cp * 2;  // c_lo, c_hi are multiples of 64: whole CTAs are valid
     __syncthreads();
-    if (c < c_hi) {
+    double a0 = 0.0, a1 = 0.0;
+    const int nsb = (rows + DB - 1) / DB;
+    const double* src = L + (int64_t)(P0 + rg * 16) * ld + c;
+    for (int sb = 0; sb < nsb; sb++, src += (int64_t)DB * ld) {
+        double2 v[16];
 #pragma unroll
-        for (int u = 0; u < 32; u++) {
-            a0 += v[u].x * ap[rg * 32 + u];
-            a1 += v[u].y * ap[rg * 32 + u];
+        for (int u = 0; u < 16; u++)
+            v[u] = (sb * DB + rg * 16 + u < rows) ? *reinterpret_cast<const double2*>(src + (int64_t)u * ld)
+                                                   : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            const double av = ap[sb * DB + rg * 16 + u];
+            a0 += v[u].x * av;
+            a1 += v[u].y * av;
         }
     }
     red[rg][cp * 2] = a0;
     red[rg][cp * 2 + 1] = a1;
     __syncthreads();
-    if (tid < BWD_PCOLS) {
-        const int cc = c_lo + blockIdx.x * BWD_PCOLS + tid;
-        if (cc < c_hi) partial[cc] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+    if (tid < BWD_UCOLS) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; g++) t += red[g][tid];
+        work[c_lo + blockIdx.x * BWD_UCOLS + tid] -= t;
     }
 }
 
-__global__ void trsv_bwd_panel_reduce_kernel(const double* partial, int64_t sPart, int n, int chunks, int c_lo, int c_hi,
-                                             double* work, int64_t sVec) {
-    const int c = c_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c_hi) return;
+// alpha = T^T z for lower-triangular T = L^-1: alpha[c] = sum_{r >= c} T[r][c] z[r].  T is streamed once by a 2-D
+// grid: CTA (column block cb of 128, row chunk k) covers rows [(cb + k*rpc) * 128, +rpc*128) of its 128 columns in
+// 128-row sub-blocks, 32 independent 16-byte loads per thread each (a column-per-CTA version was bound by its longest
+// CTA: n/8 dependent round trips at 4 loads in flight, 2.5 TB/s at n = 16 000); the chunks leave partial sums that a
+// second small kernel adds in a fixed order.  chunks <= 16 so the partials fit the backward sweep's scratch.
+constexpr int GT_CHUNKS = 2 * BWD_PCHUNKS;
+__global__ void __launch_bounds__(TRSV_THREADS)
+    gemv_t_kernel(const double* __restrict__ T, int64_t ld, int64_t sT, int n, int rpc, const double* __restrict__ z,
+                  int64_t sZ, double* partial, int64_t sPart) {
+    __shared__ double zs[DB];
+    __shared__ double red[4][DB];
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.z;
+    const int cb = blockIdx.x, k = blockIdx.y;
+    const int r_begin = (cb + k * rpc) * DB;
+    if (r_begin >= n) return;                       // uniform per CTA: this chunk lies below the matrix
+    T += b * sT;
+    z += b * sZ;
+    const int cp = tid & 63, rg = tid >> 6;         // column pair, row group (32 rows each)
+    const int c = cb * DB + 2 * cp;
+    double a0 = 0.0, a1 = 0.0;
+    for (int sb = 0; sb < rpc; sb++) {
+        const int r0 = r_begin + sb * DB;
+        if (r0 >= n) break;
+        __syncthreads();                            // zs is reused
+        if (tid < DB) zs[tid] = (r0 + tid < n) ? z[r0 + tid] : 0.0;
+        const double* src = T + (int64_t)(r0 + rg * 32) * ld + c;
+        double2 v[32];
+#pragma unroll
+        for (int u = 0; u < 32; u++)
+            v[u] = (r0 + rg * 32 + u < n) ? *reinterpret_cast<const double2*>(src + (int64_t)u * ld) : make_double2(0.0, 0.0);
+        __syncthreads();
+        if (r0 == cb * DB) {                        // diagonal block: keep r >= c only
+#pragma unroll
+            for (int u = 0; u < 32; u++) {
+                const int r = r0 + rg * 32 + u;
+                a0 += (r >= c ? v[u].x : 0.0) * zs[rg * 32 + u];
+                a1 += (r >= c + 1 ? v[u].y : 0.0) * zs[rg * 32 + u];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 32; u++) {
+                a0 += v[u].x * zs[rg * 32 + u];
+                a1 += v[u].y * zs[rg * 32 + u];
+            }
+        }
+    }
+    red[rg][2 * cp] = a0;
+    red[rg][2 * cp + 1] = a1;
+    __syncthreads();
+    if (tid < DB) {
+        const int cc = cb * DB + tid;
+        if (cc < n) partial[b * sPart + (int64_t)k * n + cc] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+    }
+}
+
+__global__ void gemv_t_reduce_kernel(const double* partial, int64_t sPart, int n, int rpc, double* alpha, int64_t sAlpha) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int nblk = (n + DB - 1) / DB, cb = c / DB;
+    const int chunks = (nblk - cb + rpc - 1) / rpc;   // chunks that exist for this column block
     const double* p = partial + (int64_t)blockIdx.y * sPart + c;
     double s = 0.0;
     for (int k = 0; k < chunks; k++) s += p[(int64_t)k * n];
-    work[(int64_t)blockIdx.y * sVec + c] -= s;
-}
-
-// alpha = T^T z for lower-triangular T = L^-1: alpha[c] = sum_{r >= c} T[r][c] z[r].  One CTA per 32 columns,
-// 8 row lanes per column; T is streamed once (32 columns = 256 contiguous bytes per row), fixed-order reduction.
-constexpr int GT_COLS = 32;
-__global__ void __launch_bounds__(256)
-    gemv_t_kernel(const double* __restrict__ T, int64_t ld, int64_t sT, int n, const double* __restrict__ z, int64_t sZ,
-                  double* alpha, int64_t sAlpha) {
-    __shared__ double red[8][GT_COLS + 1];
-    const int64_t b = blockIdx.y;
-    T += b * sT;
-    z += b * sZ;
-    alpha += b * sAlpha;
-    const int c0 = blockIdx.x * GT_COLS;
-    const int cl = threadIdx.x & (GT_COLS - 1), rl = threadIdx.x >> 5;
-    const int c = c0 + cl;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    if (c < n) {
-        const double* col = T + c;
-        int r = c0 + rl;
-        for (; r + 24 < n; r += 32) {  // 4 independent loads in flight per thread
-            const double a0 = col[(int64_t)r * ld], a1 = col[(int64_t)(r + 8) * ld];
-            const double a2 = col[(int64_t)(r + 16) * ld], a3 = col[(int64_t)(r + 24) * ld];
-            s0 += (r >= c ? a0 : 0.0) * z[r];
-            s1 += (r + 8 >= c ? a1 : 0.0) * z[r + 8];
-            s2 += (r + 16 >= c ? a2 : 0.0) * z[r + 16];
-            s3 += (r + 24 >= c ? a3 : 0.0) * z[r + 24];
-        }
-        for (; r < n; r += 8)
-            if (r >= c) s0 += col[(int64_t)r * ld] * z[r];
-    }
-    red[rl][cl] = (s0 + s1) + (s2 + s3);
-    __syncthreads();
-    if (rl == 0 && c < n) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) s += red[k][cl];
-        alpha[c] = s;
-    }
+    alpha[(int64_t)blockIdx.y * sAlpha + c] = s;
 }
 
 // dst[b][0..n) = src[b][0..n) with independent batch strides (y -> row n of the matrix, z -> work vector)
@@ -950,21 +1072,43 @@ void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* i
     CUGP_CUDA(cudaGetLastError());
 }
 
-// two partial-sum buffers: the look-ahead sweep runs the near (U1) and far (U2) panel updates concurrently
+// partial sums of gemv_t (the sweep itself needs none)
 size_t trsv_backward_scratch(int n, int batch) { return (size_t)2 * BWD_PCHUNKS * n * batch; }
 
 int trsv_backward_events(int n) { return 2 * cdiv(n, BWD_PANEL) + 2; }
 
+static int g_bwd_cluster = 1;   // 1: one cluster launch per panel chain; 0: one launch per 128-row block (the older path)
+void set_bwd_cluster(int v) { g_bwd_cluster = v; }
+
+static void launch_bwd_chain(const double* L, int64_t ld, int64_t sL, int n, int P0, int nbk, const double* invd, int64_t sInvd,
+                             const double* work, double* alpha, int64_t sVec, int batch, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        CUGP_CUDA(cudaFuncSetAttribute(trsv_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)nbk, (unsigned)batch);
+    cfg.blockDim = dim3(PC_THREADS);
+    cfg.dynamicSmemBytes = PC_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)nbk;   // <= 8: portable cluster size
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUGP_CUDA(cudaLaunchKernelEx(&cfg, trsv_bwd_chain_kernel, L, ld, sL, n, P0, nbk, invd, sInvd, work, alpha, sVec));
+}
+
 namespace {
 // work[c_lo:c_hi) -= L[P0:P0+rows, c_lo:c_hi)^T alpha[P0:P0+rows)
-void bwd_panel_update(const double* L, int64_t ld, int64_t sL, int n, int P0, int rows, int c_lo, int c_hi, double* work,
-                      const double* alpha, int64_t sVec, double* scratch, int batch, cudaStream_t st) {
+void bwd_panel_update(const double* L, int64_t ld, int64_t sL, int P0, int rows, int c_lo, int c_hi, double* work,
+                      const double* alpha, int64_t sVec, int batch, cudaStream_t st) {
     if (c_hi <= c_lo) return;
-    const int chunks = cdiv(rows, BWD_PROWS);
-    trsv_bwd_panel_kernel<<<dim3(cdiv(c_hi - c_lo, BWD_PCOLS), chunks, batch), TRSV_THREADS, 0, st>>>(
-        L, ld, sL, P0, rows, c_lo, c_hi, alpha, sVec, scratch, (int64_t)BWD_PCHUNKS * n, n);
-    trsv_bwd_panel_reduce_kernel<<<dim3(cdiv(c_hi - c_lo, 256), batch), 256, 0, st>>>(scratch, (int64_t)BWD_PCHUNKS * n, n,
-                                                                                     chunks, c_lo, c_hi, work, sVec);
+    trsv_bwd_update_kernel<<<dim3(cdiv(c_hi - c_lo, BWD_UCOLS), batch), TRSV_THREADS, 0, st>>>(L, ld, sL, P0, rows, c_lo, c_hi,
+                                                                                              alpha, work, sVec);
 }
 }  // namespace
 
@@ -980,8 +1124,7 @@ void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const 
                           cudaEvent_t* ev, int nev) {
     const int npanels = cdiv(n, BWD_PANEL);
     const bool overlap = st_chain != nullptr && npanels >= 3 && nev >= 2 * npanels + 2;
-    double* scratch1 = scratch;                                       // U1 (and the single-stream sweep)
-    double* scratch2 = scratch + (size_t)BWD_PCHUNKS * n * batch;     // U2
+    (void)scratch;
     // the caller's work vector is ready on `st`; with overlap the chain runs on `st_chain` (the high-priority
     // look-ahead stream) and the bulk updates stay on `st`
     cudaStream_t chain = overlap ? st_chain : st;
@@ -994,25 +1137,29 @@ void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const 
     for (int P1 = n; P1 > 0; p--) {
         const int P0 = ((P1 - 1) / BWD_PANEL) * BWD_PANEL;
         const int last = P0 + ((P1 - P0 - 1) / DB) * DB;
-        for (int j0 = last; j0 >= P0; j0 -= DB) {
-            const int ctas = j0 > P0 ? cdiv(j0 - P0, BWD_STEP_COLS) : 1;
-            trsv_bwd_step_kernel<<<dim3(ctas, batch), TRSV_THREADS, 0, chain>>>(L, ld, sL, n, j0, P0, invd, sInvd, work, alpha,
-                                                                               sVec);
+        if (g_bwd_cluster) {
+            launch_bwd_chain(L, ld, sL, n, P0, cdiv(P1 - P0, DB), invd, sInvd, work, alpha, sVec, batch, chain);
+        } else {
+            for (int j0 = last; j0 >= P0; j0 -= DB) {
+                const int ctas = j0 > P0 ? cdiv(j0 - P0, BWD_STEP_COLS) : 1;
+                trsv_bwd_step_kernel<<<dim3(ctas, batch), TRSV_THREADS, 0, chain>>>(L, ld, sL, n, j0, P0, invd, sInvd, work,
+                                                                                   alpha, sVec);
+            }
         }
         if (P0 > 0) {
             if (!overlap) {
-                bwd_panel_update(L, ld, sL, n, P0, P1 - P0, 0, P0, work, alpha, sVec, scratch1, batch, st);
+                bwd_panel_update(L, ld, sL, P0, P1 - P0, 0, P0, work, alpha, sVec, batch, st);
             } else {
                 const int Pm = P0 - BWD_PANEL;                      // P0 is a multiple of the panel height
                 CUGP_CUDA(cudaEventRecord(ev[2 * p], chain));       // alpha[P0:P1) is final
                 if (Pm > 0) {
                     CUGP_CUDA(cudaStreamWaitEvent(bulk, ev[2 * p], 0));
-                    bwd_panel_update(L, ld, sL, n, P0, P1 - P0, 0, Pm, work, alpha, sVec, scratch2, batch, bulk);   // U2(p)
+                    bwd_panel_update(L, ld, sL, P0, P1 - P0, 0, Pm, work, alpha, sVec, batch, bulk);   // U2(p)
                     CUGP_CUDA(cudaEventRecord(ev[2 * p + 1], bulk));
                 }
                 // U1(p) writes columns U2(p+1) also wrote (and U2(p+1) exists because P0 > 0): keep that order
                 if (p + 1 < npanels) CUGP_CUDA(cudaStreamWaitEvent(chain, ev[2 * (p + 1) + 1], 0));
-                bwd_panel_update(L, ld, sL, n, P0, P1 - P0, Pm, P0, work, alpha, sVec, scratch1, batch, chain);     // U1(p)
+                bwd_panel_update(L, ld, sL, P0, P1 - P0, Pm, P0, work, alpha, sVec, batch, chain);     // U1(p)
             }
         }
         P1 = P0;
@@ -1025,8 +1172,13 @@ void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const 
 }
 
 void launch_gemv_t(const double* T, int64_t ld, int64_t sT, int n, const double* z, int64_t sZ, double* alpha,
-                   int64_t sAlpha, int batch, cudaStream_t st) {
-    gemv_t_kernel<<<dim3(cdiv(n, GT_COLS), batch), 256, 0, st>>>(T, ld, sT, n, z, sZ, alpha, sAlpha);
+                   int64_t sAlpha, double* scratch, int batch, cudaStream_t st) {
+    const int nblk = cdiv(n, DB);
+    const int rpc = cdiv(nblk, GT_CHUNKS);            // 128-row sub-blocks per CTA; at most GT_CHUNKS chunks per column block
+    const int chunks = cdiv(nblk, rpc);
+    const int64_t sPart = (int64_t)GT_CHUNKS * n;     // == trsv_backward_scratch(n, 1)
+    gemv_t_kernel<<<dim3(nblk, chunks, batch), TRSV_THREADS, 0, st>>>(T, ld, sT, n, rpc, z, sZ, scratch, sPart);
+    gemv_t_reduce_kernel<<<dim3(cdiv(n, 256), batch), 256, 0, st>>>(scratch, sPart, n, rpc, alpha, sAlpha);
     CUGP_CUDA(cudaGetLastError());
 }
 

@@ -57,10 +57,11 @@ void launch_trsv_backward(const double* L, int64_t ld, int64_t sL, int n, const 
                           double* work, double* alpha, int64_t sVec, double* scratch, int batch, cudaStream_t st,
                           cudaStream_t st_chain = nullptr, cudaEvent_t* ev = nullptr, int nev = 0);
 int trsv_backward_events(int n);                 // events the overlapped sweep needs
+void set_bwd_cluster(int v);                     // 1 (default): one thread-block-cluster launch per panel chain
 size_t trsv_backward_scratch(int n, int batch);  // doubles needed in `scratch`
 // alpha = T^T z with T = L^-1 lower triangular: one streaming pass (used whenever T exists)
-void launch_gemv_t(const double* T, int64_t ld, int64_t sT, int n, const double* z, int64_t sZ, double* alpha,
-                   int64_t sAlpha, int batch, cudaStream_t st);
+void launch_gemv_t(const double* T, int64_t ld, int64_t sT, int n, const double* z, int64_t sZ, double* alpha, int64_t sAlpha,
+                   double* scratch /* trsv_backward_scratch(n, batch) doubles */, int batch, cudaStream_t st);
 void launch_copy_rows(const double* src, int64_t sSrc, double* dst, int64_t sDst, int n, int batch, cudaStream_t st);
 // scal[batch][4] = (u'v, logdet, LL, 0) for vectors u, v (u = v = z: quad = z'z = y'K^-1 y) with LL = -0.5*(quad + logdet + n*1.83787) (covkernel.cpp:127)
 void launch_ll_finalize(const double* y, const double* alpha, int64_t sVec, int n, const double* logdet_part,

@@ -420,6 +420,16 @@ int cugp_shardstream_predict_moments(cugp_shardstream* h, const double* Xtest, i
     CUGP_CATCH
 }
 
+int cugp_shardstream_parse_file(const char* path, int skip_tokens, size_t count, double* out) {
+    if (!path || !out || skip_tokens < 0) return CUGP_ERR_INVALID;
+    std::string err;
+    if (!parse_doubles(path, skip_tokens, count, out, &err)) {
+        set_last_error("shard reader: %s", err.c_str());
+        return CUGP_ERR_INVALID;
+    }
+    return CUGP_OK;
+}
+
 int cugp_shardstream_get_stats(cugp_shardstream* h, cugp_shardstream_stats* out) {
     if (!h || !out) return CUGP_ERR_INVALID;
     *out = h->stats;

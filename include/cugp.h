@@ -52,7 +52,9 @@ void cugp_launch_count_reset(void);
 
 /* Tuning knobs (tests and benchmarks).  "potrf_nb": outer block width of the two-level blocked Cholesky, a multiple
  * of 128, 0 = choose by matrix size; "lookahead": 1/0 panel look-ahead on a second stream; "gemm_tpc": consecutive
- * output tiles one CTA of the DMMA GEMM walks (0 = by grid size). */
+ * output tiles one CTA of the DMMA GEMM walks (0 = by grid size); "bwd_cluster": 1/0 the backward sweep's panel chain as
+ * one thread-block-cluster launch (default) or one launch per 128-row block; "graph_max_n": largest n whose
+ * theta-independent launch chains (factorisation; inverse chain) are replayed as CUDA graphs (0 = never, default 2048). */
 int cugp_set_tuning(const char *key, long value);
 
 /* ---- Covsum (cpp_serial_gp/covkernel.h:3-38) ------------------------------------------------------ */
@@ -194,6 +196,10 @@ int cugp_shardstream_loglik_grad_local(cugp_shardstream *h, int want_grad, doubl
 int cugp_shardstream_predict_moments_dev(cugp_shardstream *h, const double *Xtest, int m, double *PQ_dev);
 int cugp_shardstream_predict_moments(cugp_shardstream *h, const double *Xtest, int m, double *PQ);
 int cugp_shardstream_get_stats(cugp_shardstream *h, cugp_shardstream_stats *out);
+/* The reader's text parser alone (host only, no device needed): skip `skip_tokens` whitespace/comma separated tokens
+ * (2 for the "n d" header of an input shard, 0 for a label file), then read `count` doubles; CUGP_ERR_INVALID with
+ * the file name in cugp_last_error() when the file is missing or short. */
+int cugp_shardstream_parse_file(const char *path, int skip_tokens, size_t count, double *out);
 
 /* ---- measurement helpers (bench.py) ----------------------------------------------------------------- */
 /* Sustained FP64 DMMA (mma.sync.m8n8k4.f64) and DFMA throughput of this GPU in TFLOP/s, register resident,

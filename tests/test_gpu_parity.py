@@ -145,7 +145,7 @@ def test_lookahead_is_bitwise_neutral(n, nb):
     assert np.linalg.norm(L1 - Lo) <= 1e-12 * np.linalg.norm(Lo)
 
 
-@pytest.mark.parametrize("n", [3300, 4200])
+@pytest.mark.parametrize("n", [700, 3300, 4200])
 def test_backward_sweep_lookahead_is_bitwise_neutral(n):
     """alpha = L^-T z on the blocked sweep (no T at hand): with look-ahead the far part of every 1024-row panel update
     runs on the main stream while the next panel's block steps run on the chain stream; every entry of the work vector
@@ -155,20 +155,66 @@ def test_backward_sweep_lookahead_is_bitwise_neutral(n):
     th = [3.762111, -1.152105, -0.384461]
     g = cg.Covsum(n, 10)
     g.set_data(X, y)
-    out = []
+    out = {}
     try:
-        for la in (0, 1):
-            lib().cugp_set_tuning(b"lookahead", la)
-            g.set_loghyperparam([th[0] + 1e-9 * la, th[1], th[2]])   # new theta: refactorise, no cached alpha
-            g.set_loghyperparam(th)
-            out.append(g.alpha_resident().copy())
+        for cl in (0, 1):        # panel chain: one launch per 128-row block / one thread-block-cluster launch per panel
+            for la in (0, 1):
+                lib().cugp_set_tuning(b"bwd_cluster", cl)
+                lib().cugp_set_tuning(b"lookahead", la)
+                g.set_loghyperparam([th[0] + 1e-9, th[1], th[2]])   # new theta: refactorise, no cached alpha
+                g.set_loghyperparam(th)
+                out[cl, la] = g.alpha_resident().copy()
     finally:
         lib().cugp_set_tuning(b"lookahead", 1)
-    assert np.array_equal(out[0], out[1])
+        lib().cugp_set_tuning(b"bwd_cluster", 1)
+    assert np.array_equal(out[0, 0], out[0, 1]) and np.array_equal(out[1, 0], out[1, 1])
+    # the cluster kernel sums the 128x128 mat-vec in a different (fixed) order than the per-block kernel
+    assert np.linalg.norm(out[1, 1] - out[0, 1]) <= 1e-11 * np.linalg.norm(out[0, 1])
     K = g.compute_K_train(X)
-    r = K @ out[1] - y
-    assert np.linalg.norm(r) <= 1e-9 * np.linalg.norm(y)
+    for a in (out[0, 1], out[1, 1]):
+        assert np.linalg.norm(K @ a - y) <= 1e-9 * np.linalg.norm(y)
     g.close()
+
+
+@pytest.mark.parametrize("n,B", [(700, 1), (1500, 1), (600, 3)])
+def test_graph_replay_is_bitwise_neutral(n, B):
+    """The factorisation and the inverse chain (TRTRI, alpha, LAUUM) are replayed as CUDA graphs from the second
+    evaluation on: same kernels, same arguments, same order per stream -- LL, gradient and predictions must not change
+    by a bit against direct launches, across several thetas (the graphs are theta independent) and for a batch."""
+    from cugp_b200.loaders import synthetic_sine
+    X, y = synthetic_sine(n * B + 16, 10)
+    Xt = X[n * B:]
+    thetas = [[3.762111, -1.152105, -0.384461], [2.0, 2.0, 2.0], [0.882908, 0.098703, -2.971479], [3.0, 0.5, -1.0]]
+    res = {}
+    try:
+        for mode, max_n in (("direct", 0), ("graph", 16384)):
+            lib().cugp_set_tuning(b"graph_max_n", max_n)
+            out = []
+            if B == 1:
+                g = cg.Covsum(n, 10)
+                g.set_data(X[:n], y[:n])
+                for th in thetas:
+                    g.set_loghyperparam(th)
+                    out.append((g.loglik_resident(), g.grad_resident().copy()))
+                mu, var = g.compute_test_means_and_variances(X[:n], y[:n], Xt)
+                out.append((mu.copy(), var.copy()))
+                g.close()
+            else:
+                b = cg.BCM(X[:n * B], y[:n * B], K=B, rank=0, world=1)
+                for th in thetas:
+                    b.set_BCM_log_hyperparam(th)
+                    ll, gr = b.loglik_and_gradient()
+                    out.append((ll, gr.copy()))
+                mu, var = b.compute_BCM_test_means_and_var(Xt)
+                out.append((mu.copy(), var.copy()))
+                b.close()
+            res[mode] = out
+    finally:
+        lib().cugp_set_tuning(b"graph_max_n", 2048)
+    for a, b_ in zip(res["direct"], res["graph"]):
+        assert np.array_equal(np.asarray(a[0]), np.asarray(b_[0])) and np.array_equal(a[1], b_[1])
+    ref = PORT.loglik(X[:n], y[:n], thetas[1]) if B == 1 else PORT.bcm_loglik(X[:n * B], y[:n * B], B, thetas[1])
+    assert_ll(res["graph"][1][0], ref)
 
 
 def test_non_pd_is_nan_not_an_error():

@@ -141,6 +141,41 @@ def test_stream_missing_shard_is_an_error(tmp_path):
     s.close()
 
 
+# ---- the reader's parser (CPU) ------------------------------------------------------------------------------
+def test_parser_matches_numpy_on_reference_and_generated_files(tmp_path):
+    """from_chars must read exactly what fscanf("%lf") / numpy read: header skipped, exponents, signs, commas, CRLF."""
+    import ctypes as C
+    from cugp_b200._lib import lib, ptr
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((37, 5)) * 10.0 ** rng.integers(-30, 30, (37, 5))
+    X[0, 0], X[1, 1], X[2, 2] = 0.0, -0.0, 5e-324
+    inp, lab, n = _write_shards(tmp_path, X, X[:, 0], 1)
+    out = np.full(X.size, np.nan)
+    assert lib().cugp_shardstream_parse_file((inp + "0.txt").encode(), 2, X.size, ptr(out)) == 0
+    assert np.array_equal(out.reshape(X.shape), X) and np.signbit(out[6])
+    yl = np.full(n, np.nan)
+    assert lib().cugp_shardstream_parse_file((lab + "0.txt").encode(), 0, n, ptr(yl)) == 0
+    assert np.array_equal(yl, X[:, 0])
+    # "+" signs, commas, CRLF, upper-case exponent
+    with open(tmp_path / "odd.txt", "w", newline="") as f:
+        f.write("3 2\r\n+1.5,2E3\r\n-3e-2\t4\r\n5 , 6\r\n")
+    o = np.zeros(6)
+    assert lib().cugp_shardstream_parse_file(str(tmp_path / "odd.txt").encode(), 2, 6, ptr(o)) == 0
+    assert o.tolist() == [1.5, 2000.0, -0.03, 4.0, 5.0, 6.0]
+    # short and missing files are errors that name the file
+    assert lib().cugp_shardstream_parse_file(str(tmp_path / "odd.txt").encode(), 2, 7, ptr(np.zeros(7))) != 0
+    assert b"odd.txt" in lib().cugp_last_error()
+    assert lib().cugp_shardstream_parse_file(str(tmp_path / "nope.txt").encode(), 0, 1, ptr(np.zeros(1))) != 0
+    assert b"cannot open" in lib().cugp_last_error()
+    ref = "/root/reference/scaling_dataset/si24000_16sharded_chunk3.txt"
+    if os.path.exists(ref):     # this container only: the reference's own shard file
+        from cugp_b200.loaders import load_inputs
+        Xr = load_inputs(ref)
+        o = np.zeros(Xr.size)
+        assert lib().cugp_shardstream_parse_file(ref.encode(), 2, Xr.size, ptr(o)) == 0
+        assert np.array_equal(o.reshape(Xr.shape), Xr)
+
+
 # ---- host logic over gloo (CPU) ---------------------------------------------------------------------------
 class OracleStreamLocal:
     """Stand-in for the C-ABI stream of one rank, evaluated with the CPU oracle (test infrastructure)."""

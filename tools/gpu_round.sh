@@ -14,7 +14,4 @@ fi
 if [ "${NCU:-1}" = "1" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_COUNT:-3000} --csv --log-file gpurun_out/launches_bench.csv \
    python bench.py --steps 1 --warmup 3 --no-extra ${BENCH_ARGS:-} > gpurun_out/ncu_bench.log 2>&1; echo "ncu_list_rc=$?"
-timeout 120 python tools/chol_only.py 40000 1 > gpurun_out/chol_only_plain.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:dgemm_ws_kernel<.int.128, .int.128' -s 7 -c 1 -o gpurun_out/trailing_full -f \
-   python tools/chol_only.py 40000 1 > gpurun_out/ncu_full.log 2>&1; echo "ncu_full_rc=$?"
 fi
