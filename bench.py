@@ -468,6 +468,9 @@ def main():
                   "n": 24000, "d": 10, "experts": 16, "parallelism": f"experts e%{world} per rank, allreduce(4) + allreduce(2m)",
                   "l2": "256 MB flush between steps"}
         b.close()
+        # the two halves of the step on their own: prediction with the factorised experts resident (the metric's name)
+        # and the (LL, gradient) evaluation, each max-over-ranks
+        out["phases"] = extra_c4(cg, torch, dist, flush, m=a.m)
 
     extra = None
     if not a.no_extra and a.workload == "c5":   # collective: every rank takes part in the sharded BCM
@@ -497,13 +500,17 @@ def main():
         cublas = None
     if syrk_cnt:
         achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
-        traffic = None
+        traffic = traffic_detail = None
         tp = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp))
+            # one ncu --set full capture of ONE launch of this kernel (the first full-width update of an n = 40 000
+            # factorisation): its DRAM bytes next to the algorithmic bytes of that same launch
+            traffic_detail = json.load(open(tp))
+            traffic = traffic_detail.get("dram_bytes_total")
         out["roofline"] = {"bound": "tensor", "kernel": "dgemm_ws_kernel<128,128> (Cholesky trailing update A22 -= P P^T, lower "
                                                         "tiles, K = outer block width)",
                            "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma, "traffic": traffic,
+                           "traffic_detail": traffic_detail,
                            "peak_source": "measured here, sustained: one 2 s launch of register-resident mma.sync.m8n8k4.f64 "
                                           "(cugp_probe_dmma); MEASURED_PEAKS.json has no FP64 entry",
                            "frac_of_nominal_37": achieved / NOMINAL_FP64_TFLOPS,
