@@ -241,13 +241,19 @@ def extra_c2(cg, torch, flush, n=4096, evals=6):
     return 1.0 / statistics.median(ts[2:])
 
 
-def extra_c4(cg, torch, dist, flush, m=10000, reps=4):
+def extra_c4(cg, torch, dist, flush, m=10000, reps=4, experts=16, prefix="c4"):
     """BCM 16 x 1500 on ALL ranks of this run (experts e % world == rank, NCCL allreduce of the moments):
-    prediction pts/s with factorised experts resident, and (LL, gradient) evaluations/s; theta_C."""
-    d = np.load(os.path.join(ROOT, "tests", "golden", "data_si24000.npz"))
+    prediction pts/s with factorised experts resident, and (LL, gradient) evaluations/s; theta_C.
+    experts != 16: the same generator at `experts` x 1500 synthetic rows (an ensemble large enough that eight GPUs still
+    hold several experts each)."""
     from cugp_b200.loaders import synthetic_sine
+    if experts == 16:
+        d = np.load(os.path.join(ROOT, "tests", "golden", "data_si24000.npz"))
+        Xall, yall = d["X"], d["y"]
+    else:
+        Xall, yall = synthetic_sine(experts * 1500, 10, seed=11)
     Xt, _ = synthetic_sine(m, 10, seed=7)
-    b = cg.BCM(d["X"], d["y"], K=16)
+    b = cg.BCM(Xall, yall, K=experts)
     b.set_BCM_log_hyperparam(TH_C)
     b.loglik_and_gradient()
     b.compute_BCM_test_means_and_var(Xt)
@@ -280,8 +286,8 @@ def extra_c4(cg, torch, dist, flush, m=10000, reps=4):
     t_pred = timed(lambda: b.compute_BCM_test_means_and_var(Xt))
     t_eval = timed(ev)
     b.close()
-    return {"c4_bcm_pred_pts_per_s": m / t_pred, "c4_bcm_loglik_grad_evals_per_s": 1.0 / t_eval, "c4_gpus": b.world,
-            "c4_test_points": m}
+    return {f"{prefix}_bcm_pred_pts_per_s": m / t_pred, f"{prefix}_bcm_loglik_grad_evals_per_s": 1.0 / t_eval,
+            f"{prefix}_gpus": b.world, f"{prefix}_test_points": m, f"{prefix}_experts_x_rows": f"{experts} x 1500"}
 
 
 def extra_f3(cg, torch, dist, flush, chunks=32, n=2000, d=7, slots=8, passes=3):
@@ -471,11 +477,14 @@ def main():
         # the two halves of the step on their own: prediction with the factorised experts resident (the metric's name)
         # and the (LL, gradient) evaluation, each max-over-ranks
         out["phases"] = extra_c4(cg, torch, dist, flush, m=a.m)
+        # the same ensemble shape at 64 experts (96 000 rows): eight GPUs still hold eight experts each
+        out["phases"].update(extra_c4(cg, torch, dist, flush, m=a.m, experts=64, prefix="c4x4"))
 
     extra = None
     if not a.no_extra and a.workload == "c5":   # collective: every rank takes part in the sharded BCM
         try:
             extra = extra_c4(cg, torch, dist, flush)
+            extra.update(extra_c4(cg, torch, dist, flush, experts=64, prefix="c4x4"))
         except Exception as e:  # the headline must still print
             extra = {"error": repr(e)}
     if rank != 0:
