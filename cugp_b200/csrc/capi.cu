@@ -131,6 +131,16 @@ int cugp_set_tuning(const char* key, long value) {
         bump_tuning_epoch();
         return CUGP_OK;
     }
+    if (std::strcmp(key, "overlap_inv_max_n") == 0) {
+        if (value < 0) return CUGP_ERR_INVALID;
+        set_overlap_inverse((int)value, 0);
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "overlap_inv_cap") == 0) {
+        if (value <= 0 || value > 1024) return CUGP_ERR_INVALID;
+        set_overlap_inverse(-1, (int)value);
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "gemm_raster") == 0) {
         if (value < 0 || value > 256) return CUGP_ERR_INVALID;
         set_gemm_raster_width((int)value);

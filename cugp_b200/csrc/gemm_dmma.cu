@@ -435,9 +435,14 @@ void launch_ws(const GemmParams& p_in, cudaStream_t stream) {
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
         return v > 0 ? v : 148;
     }();
+    int stride = tpc > 1 ? sms : 1;
+    if (p.max_ctas > 0 && total > p.max_ctas) {   // one round of max_ctas CTAs walks everything
+        stride = p.max_ctas;
+        tpc = (int)((total + stride - 1) / stride);
+    }
     p.tiles_per_mat = tiles;
     p.tiles_per_cta = tpc;
-    p.cta_stride = tpc > 1 ? sms : 1;
+    p.cta_stride = stride;
     p.raster_w = g_raster_w;
     const int64_t per_round = (int64_t)p.cta_stride * tpc;   // tiles one round of cta_stride CTAs covers
     const int64_t rounds = (total + per_round - 1) / per_round;

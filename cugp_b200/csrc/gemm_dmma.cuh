@@ -31,6 +31,8 @@ struct GemmParams {
     int khi_ti, khi_tj;      // restrict k <  (ti+1)*BM / (tj+1)*BN
     double* colsumsq;        // non-null: write per-row-tile column sums of squares [tiles_m][N] instead of C
     int64_t sCss;            // batch stride of colsumsq
+    int max_ctas;            // > 0: the launch uses at most this many CTAs (= SMs), each walking more tiles -- background
+                             // work that must leave SMs free for a latency-critical stream
     int64_t tiles_per_mat;   // filled by the launcher: output tiles of one matrix (raster order)
     int tiles_per_cta;       // filled by the launcher: work items (tile, batch) one CTA walks
     int cta_stride;          // filled by the launcher: distance between a CTA's successive tiles (SM count; 1 if tpc == 1)

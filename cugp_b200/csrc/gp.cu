@@ -47,6 +47,16 @@ void bump_tuning_epoch() { g_epoch++; }
 // the look-ahead relies on
 static int g_graph_max_n = 2048;
 void set_graph_max_n(int n) { g_graph_max_n = n; bump_tuning_epoch(); }
+// Inverse overlapped with the factorisation: only where the factorisation is bound by its chain of block steps and
+// leaves SMs idle.  Measured (profiles/r1_overlap_inverse.txt, LL + gradient per evaluation): n = 3000 3.02 -> 2.68 ms,
+// 4096 4.54 -> 4.22, 6000 10.45 -> 10.06, 8192 21.0 -> 22.0 (slower), 16 x 1500 3.75 -> 3.60.  Capping the background
+// GEMMs to fewer SMs (32 / 64 / 96) only made the background the bottleneck, so the default cap is the whole chip.
+static int g_overlap_max_n = 6144, g_overlap_cap = 148;
+void set_overlap_inverse(int max_n, int cap) {
+    if (max_n >= 0) g_overlap_max_n = max_n;
+    if (cap > 0) g_overlap_cap = cap;
+    bump_tuning_epoch();
+}
 static int g_lookahead = 1;
 void set_lookahead(int v) { g_lookahead = v; bump_tuning_epoch(); }
 bool lookahead_enabled() { return g_lookahead != 0; }
@@ -138,6 +148,7 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
     const int nblk = cdiv(n, kDiag);
     const int NB = potrf_outer_width(n);
     const int npanels = cdiv(n, NB);
+    if (la) la->panel_events = false;
     if (!la || !la->st2 || npanels < 3 || !lookahead_enabled()) {
         for (int J0 = 0; J0 < n; J0 += NB) {
             const int Jend = std::min(n, J0 + NB);
@@ -175,10 +186,11 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
     }
     CUGP_CUDA(cudaEventRecord(ev_end, s2));
     CUGP_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
+    la->panel_events = true;
 }
 
 void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t sM, int n, const double* invd,
-                     int64_t sInvd, int batch, cudaStream_t st, long* launches) {
+                     int64_t sInvd, int batch, cudaStream_t st, long* launches, int max_ctas) {
     launch_scatter_invdiag(invd, sInvd, T, ld, sM, n, batch, st);
     if (launches) ++*launches;
     for (int64_t h = kDiag; h < n; h *= 2) {
@@ -210,6 +222,7 @@ void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t 
             p.sA = p.sB = p.sC = pair_stride;
             p.sA2 = p.sB2 = p.sC2 = sM;
             p.klo_tj = 1;
+            p.max_ctas = max_ctas;
             if (npairs == 1) { p.batch_inner = 0; p.sA = p.sB = p.sC = sM; }
             GemmConfig cfg = pick_config(n2, (int)h, tot, false);
             launch_gemm(p, true, false, cfg, st);
@@ -223,6 +236,7 @@ void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t 
             q.sA = q.sB = q.sC = pair_stride;
             q.sA2 = q.sB2 = q.sC2 = sM;
             q.khi_ti = 1;
+            q.max_ctas = max_ctas;
             if (npairs == 1) { q.batch_inner = 0; q.sA = q.sB = q.sC = sM; }
             launch_gemm(q, true, false, cfg, st);
             if (launches) *launches += 2;
@@ -280,6 +294,11 @@ GpBatch::~GpBatch() {
         cudaStreamSynchronize(la.st2);
         cudaStreamDestroy(la.st2);
     }
+    if (st3) {
+        cudaStreamSynchronize(st3);
+        cudaStreamDestroy(st3);
+    }
+    if (ev_T) cudaEventDestroy(ev_T);
     if (own_stream && st) cudaStreamDestroy(st);
 }
 
@@ -401,6 +420,7 @@ bool GpBatch::run_graphed(std::map<int, GraphEntry>& cache, F&& body) {
     }
     CUGP_CUDA(cudaGraphLaunch(e.exec, st));
     launches += e.launches;
+    la.panel_events = false;   // the per-panel events were graph nodes, not records another stream can wait on
     return true;
 }
 
@@ -449,11 +469,70 @@ void GpBatch::prof_collect(double* ms, double* flops, long* count) {
     if (count) *count = prof.count;
 }
 
+void GpBatch::join_T() {
+    if (!t_inflight) return;
+    CUGP_CUDA(cudaStreamWaitEvent(st, ev_T, 0));
+    t_inflight = false;
+}
+
+// T = L^-1 in row groups of 512, each enqueued on a third stream behind the event "the panel holding the group's last
+// column is final":  T_gg by recursive doubling inside the group, then  T[g, 0:r0] = -T_gg (L[g, 0:r0] T[0:r0, 0:r0])
+// (a left-looking block row: it needs only rows 0..r1 of L and the groups above).  While the factorisation is a chain
+// of 128-column block steps (n <~ 6000: 2.5 ms for 0.65 ms worth of flops at n = 4096) the other SMs do this work; the
+// GEMMs are capped to g_overlap_cap CTAs so the chain's high-priority launches always find free SMs.  The last group
+// can only start when the chain has ended and runs uncapped.
+void GpBatch::enqueue_trtri_overlapped() {
+    const int NB = potrf_outer_width(n);
+    constexpr int G = 512;
+    if (!st3) {
+        CUGP_CUDA(cudaStreamCreateWithFlags(&st3, cudaStreamNonBlocking));
+        CUGP_CUDA(cudaEventCreateWithFlags(&ev_T, cudaEventDisableTiming));
+    }
+    const int64_t sI = (int64_t)nblk * kDiag * kDiag;
+    for (int r0 = 0; r0 < n; r0 += G) {
+        const int r1 = std::min(n, r0 + G), rows = r1 - r0;
+        CUGP_CUDA(cudaStreamWaitEvent(st3, la.ev[2 * ((r1 - 1) / NB)], 0));
+        const int cap = r1 == n ? 0 : g_overlap_cap;
+        const int64_t o = (int64_t)r0 * (ld + 1);
+        trtri_recursive(Kb + o, Tb + o, Wb + o, ld, mat_stride(), rows, invd + (int64_t)(r0 / kDiag) * kDiag * kDiag, sI, B, st3,
+                        &launches, cap);
+        if (r0 == 0) continue;
+        GemmParams p{};  // tmp = L[g, 0:r0] T[0:r0, 0:r0]   (T lower: k >= column tile start)
+        p.A = Kb + (int64_t)r0 * ld; p.lda = ld; p.sA = mat_stride();
+        p.B = Tb; p.ldb = ld; p.sB = mat_stride();
+        p.C = Wb + (int64_t)r0 * ld; p.ldc = ld; p.sC = mat_stride();
+        p.M = rows; p.N = r0; p.K = r0;
+        p.alpha = 1.0; p.beta = 0.0;
+        p.batch = B;
+        p.klo_tj = 1;
+        p.max_ctas = cap;
+        const GemmConfig cfg = pick_config(rows, r0, B, false);
+        launch_gemm(p, true, false, cfg, st3);
+        GemmParams q{};  // T[g, 0:r0] = -T_gg tmp   (T_gg lower: k < row tile end)
+        q.A = Tb + o; q.lda = ld; q.sA = mat_stride();
+        q.B = Wb + (int64_t)r0 * ld; q.ldb = ld; q.sB = mat_stride();
+        q.C = Tb + (int64_t)r0 * ld; q.ldc = ld; q.sC = mat_stride();
+        q.M = rows; q.N = r0; q.K = rows;
+        q.alpha = -1.0; q.beta = 0.0;
+        q.batch = B;
+        q.khi_ti = 1;
+        q.max_ctas = cap;
+        launch_gemm(q, true, false, cfg, st3);
+        launches += 2;
+    }
+    CUGP_CUDA(cudaEventRecord(ev_T, st3));
+    t_inflight = true;
+    t_valid = true;
+}
+
 void GpBatch::factorize() {
     if (have_L) return;
+    join_T();       // an earlier inverse may still be reading L on the third stream
     build_K(0);
     potrf_with_rhs();
     have_L = true;
+    // a batch that has computed gradients / predictions before (T exists) will want T = L^-1 again: start it now
+    if (Tb && Wb && la.panel_events && n <= g_overlap_max_n) enqueue_trtri_overlapped();
 }
 
 // alpha = L^-T z.  With T = L^-1 at hand (gradient / prediction paths) it is one streaming pass alpha = T^T z;
@@ -489,6 +568,14 @@ void GpBatch::ensure_TW() {
 void GpBatch::trtri() {
     if (have_T) return;
     factorize();
+    if (t_valid) {   // computed alongside the factorisation
+        join_T();
+        t_valid = false;
+        have_T = true;
+        have_Kinv = false;
+        return;
+    }
+    join_T();
     ensure_TW();
     trtri_recursive(Kb, Tb, Wb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, B, st, &launches);
     have_T = true;

@@ -16,6 +16,7 @@ namespace cugp {
 struct PotrfLookahead {
     cudaStream_t st2 = nullptr;
     std::vector<cudaEvent_t> ev;
+    bool panel_events = false;   // the last potrf_blocked call took the look-ahead path: ev[2J] = "panel J is final"
 };
 
 struct GpBatch {
@@ -58,6 +59,13 @@ struct GpBatch {
     } prof;
     PotrfLookahead la;
     std::vector<cudaEvent_t> bwd_ev;       // events of the overlapped backward sweep
+    // T = L^-1 computed group by group on a third stream WHILE the factorisation's chain of block steps advances
+    // (see enqueue_trtri_overlapped): t_valid = the work in flight belongs to the current (data, theta).
+    cudaStream_t st3 = nullptr;
+    cudaEvent_t ev_T = nullptr;
+    bool t_inflight = false, t_valid = false;
+    void enqueue_trtri_overlapped();
+    void join_T();                         // main stream waits for the third stream
     // CUDA graphs of the theta-independent launch chains (small and medium n are bound by the chain of dependent
     // launches across two streams, not by any kernel): captured on the second use, keyed by the active batch count.
     struct GraphEntry {
@@ -89,7 +97,12 @@ struct GpBatch {
     void eval_launch(bool want_grad);
     void eval_collect(double* ll_out, double* g_out);
     void set_theta(const double th[3]);
-    void invalidate() { have_L = have_alpha = have_T = have_Kinv = false; }
+    // Every path that is about to overwrite Kb / Tb / Wb goes through here first: the main stream is made to wait for
+    // an inverse still running on the third stream, then the cached state is dropped.
+    void invalidate() {
+        join_T();
+        have_L = have_alpha = have_T = have_Kinv = t_valid = false;
+    }
 
     void build_K(int full);                 // K1 into Kb
     void potrf(bool with_rhs = false);      // K2 on Kb (expects K in the lower triangle; with_rhs: row n rides along)
@@ -129,6 +142,8 @@ int potrf_outer_width(int n);
 void set_potrf_outer_width(int nb);
 // T = L^-1 by recursive doubling over 128-blocks (W is n x n scratch).
 void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t sM, int n, const double* invd,
-                     int64_t sInvd, int batch, cudaStream_t st, long* launches);
+                     int64_t sInvd, int batch, cudaStream_t st, long* launches, int max_ctas = 0);
+// Overlap of the inverse with the factorisation: largest n it is used for (0 = never) and the SMs its GEMMs may occupy.
+void set_overlap_inverse(int max_n, int cap);
 
 }  // namespace cugp

@@ -54,7 +54,9 @@ void cugp_launch_count_reset(void);
  * of 128, 0 = choose by matrix size; "lookahead": 1/0 panel look-ahead on a second stream; "gemm_tpc": consecutive
  * output tiles one CTA of the DMMA GEMM walks (0 = by grid size); "bwd_cluster": 1/0 the backward sweep's panel chain as
  * one thread-block-cluster launch (default) or one launch per 128-row block; "graph_max_n": largest n whose
- * theta-independent launch chains (factorisation; inverse chain) are replayed as CUDA graphs (0 = never, default 2048). */
+ * theta-independent launch chains (factorisation; inverse chain) are replayed as CUDA graphs (0 = never, default 2048);
+ * "overlap_inv_max_n": largest n for which T = L^-1 is computed on a third stream while the factorisation advances
+ * (0 = never, default 6144), "overlap_inv_cap": SMs those background GEMMs may occupy (default: all). */
 int cugp_set_tuning(const char *key, long value);
 
 /* ---- Covsum (cpp_serial_gp/covkernel.h:3-38) ------------------------------------------------------ */

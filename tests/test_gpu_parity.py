@@ -217,6 +217,52 @@ def test_graph_replay_is_bitwise_neutral(n, B):
     assert_ll(res["graph"][1][0], ref)
 
 
+@pytest.mark.parametrize("n,B", [(2300, 1), (3000, 2)])
+def test_overlapped_inverse_matches_sequential(n, B):
+    """T = L^-1 computed in row groups on a third stream while the factorisation advances (tuning overlap_inv_max_n)
+    against the sequential recursive doubling: same K^-1 up to rounding, so gradient and predictions agree to 1e-11;
+    repeated over thetas (every evaluation after the first takes the overlapped path) and capped / uncapped."""
+    from cugp_b200.loaders import synthetic_sine
+    X, y = synthetic_sine(n * B + 16, 10)
+    Xt = X[n * B:]
+    thetas = [[3.762111, -1.152105, -0.384461], [2.0, 2.0, 2.0], [3.0, 0.5, -1.0]]
+    res = {}
+    try:
+        for mode, max_n, cap in (("seq", 0, 64), ("ovl64", 8192, 64), ("ovl8", 8192, 8)):
+            lib().cugp_set_tuning(b"overlap_inv_max_n", max_n)
+            lib().cugp_set_tuning(b"overlap_inv_cap", cap)
+            out = []
+            if B == 1:
+                g = cg.Covsum(n, 10)
+                g.set_data(X[:n], y[:n])
+                for th in thetas + thetas[:1]:
+                    g.set_loghyperparam(th)
+                    out.append((g.loglik_resident(), g.grad_resident().copy()))
+                mu, var = g.compute_test_means_and_variances(X[:n], y[:n], Xt)
+                out.append((mu.copy(), var.copy()))
+                g.close()
+            else:
+                b = cg.BCM(X[:n * B], y[:n * B], K=B, rank=0, world=1)
+                for th in thetas + thetas[:1]:
+                    b.set_BCM_log_hyperparam(th)
+                    ll, gr = b.loglik_and_gradient()
+                    out.append((ll, gr.copy()))
+                mu, var = b.compute_BCM_test_means_and_var(Xt)
+                out.append((mu.copy(), var.copy()))
+                b.close()
+            res[mode] = out
+    finally:
+        lib().cugp_set_tuning(b"overlap_inv_max_n", OVERLAP_DEFAULT)
+        lib().cugp_set_tuning(b"overlap_inv_cap", 148)
+    for mode in ("ovl64", "ovl8"):
+        for a, b_ in zip(res["seq"], res[mode]):
+            assert np.array_equal(np.asarray(a[0]), np.asarray(b_[0])) or np.allclose(a[0], b_[0], rtol=1e-11, atol=0)
+            assert_grad(b_[1], a[1], 1e-10) if np.asarray(a[1]).shape == (3,) else np.testing.assert_allclose(b_[1], a[1], rtol=1e-10)
+    # first and last evaluation use the same theta: the overlapped path must reproduce itself
+    assert res["ovl64"][0][0] == res["ovl64"][3][0]
+    assert_grad(res["ovl64"][3][1], res["ovl64"][0][1], 1e-11)
+
+
 def test_non_pd_is_nan_not_an_error():
     """sqrt of a negative pivot gives NaN that propagates; status stays OK (matrixops.cpp:77)."""
     A = np.array([[1.0, 2.0], [2.0, 1.0]])
@@ -252,6 +298,8 @@ def test_K_train_and_k_test(n, d):
 
 
 # ---------------------------------------------------------------------------------------------- golden cases
+OVERLAP_DEFAULT = 6144   # library default of the tuning key overlap_inv_max_n
+
 COVSUM = [n for n, c in GOLD.items() if c["kind"] == "covsum"]
 BCMS = [n for n, c in GOLD.items() if c["kind"] == "bcm"]
 
