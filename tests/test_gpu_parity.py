@@ -187,6 +187,7 @@ def test_graph_replay_is_bitwise_neutral(n, B):
     thetas = [[3.762111, -1.152105, -0.384461], [2.0, 2.0, 2.0], [0.882908, 0.098703, -2.971479], [3.0, 0.5, -1.0]]
     res = {}
     try:
+        lib().cugp_set_tuning(b"overlap_inv_max_n", 0)     # graph replay in isolation: the inverse stays sequential
         for mode, max_n in (("direct", 0), ("graph", 16384)):
             lib().cugp_set_tuning(b"graph_max_n", max_n)
             out = []
@@ -211,6 +212,7 @@ def test_graph_replay_is_bitwise_neutral(n, B):
             res[mode] = out
     finally:
         lib().cugp_set_tuning(b"graph_max_n", 2048)
+        lib().cugp_set_tuning(b"overlap_inv_max_n", OVERLAP_DEFAULT)
     for a, b_ in zip(res["direct"], res["graph"]):
         assert np.array_equal(np.asarray(a[0]), np.asarray(b_[0])) and np.array_equal(a[1], b_[1])
     ref = PORT.loglik(X[:n], y[:n], thetas[1]) if B == 1 else PORT.bcm_loglik(X[:n * B], y[:n * B], B, thetas[1])
