@@ -309,7 +309,10 @@ def extra_f3(cg, torch, dist, flush, chunks=32, n=2000, d=7, slots=8, passes=3):
             np.savetxt(os.path.join(tmp, f"lab_{i}.txt"), y[i * n:(i + 1) * n], fmt="%.17g")
     if dist is not None:
         dist.barrier()
-    s = cg.ShardStream.from_files(os.path.join(tmp, "in_"), os.path.join(tmp, "lab_"), chunks, n, d, slots=slots)
+    # dist is None: this process alone walks all shards (rank 0 / world 1 stated explicitly: a process group may still
+    # be initialised when rank 0 runs its rank-0-only legs)
+    rw = {} if dist is not None else {"rank": 0, "world": 1}
+    s = cg.ShardStream.from_files(os.path.join(tmp, "in_"), os.path.join(tmp, "lab_"), chunks, n, d, slots=slots, **rw)
     ts = []
     for i in range(passes + 1):
         s.set_BCM_log_hyperparam([TH_C[0] + 1e-7 * i, TH_C[1], TH_C[2]])
@@ -344,7 +347,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c5", choices=["c5", "c3", "c2", "c4"])
-    ap.add_argument("--n", type=int, default=None, help="override the row count of the workload")
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=None,
+                    help="override the row count of the workload (use --rows under torchrun: its parser claims --n)")
     ap.add_argument("--m", type=int, default=10000, help="test points (c3/c4)")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-extra", action="store_true")
@@ -536,7 +540,8 @@ def main():
         except Exception as e:
             extra = dict(extra or {}, c2_error=repr(e))
         try:
-            extra.update(extra_f3(cg, torch, dist, flush))   # collective: shards i % world == rank, allreduce(4)
+            # rank 0 only from here on (the other ranks have left): the stream runs un-sharded, no collective
+            extra.update(extra_f3(cg, torch, None, flush))
         except Exception as e:
             extra["f3_error"] = repr(e)
         out["extra"] = extra
