@@ -3,7 +3,8 @@
 //   K5a cross covariance fused with the predictive-mean partials
 //   K4  fused gradient trace (K and D rebuilt on the fly, Kinv streamed once)
 //   K2a 128x128 diagonal-block Cholesky + triangular inverse (one CTA, shared memory)
-//   K3  blocked triangular solves (forward / backward), log-likelihood finalisation
+//   K3  backward sweep alpha = L^-T z: thread-block-cluster panel chain (DSMEM) + single-owner panel updates,
+//       alpha = T^T z streaming pass, log-likelihood finalisation
 // Every reduction is a fixed-shape tree over per-CTA partials: results are run-to-run deterministic.
 #include "kernels.cuh"
 
@@ -594,12 +595,12 @@ __global__ void __launch_bounds__(DIAG_THREADS, 1)
 // ------------------------------------------------------------------------------------------------
 // K3: triangular solves.  The forward substitution L z = y is fused into the Cholesky (y^T is row n of the
 // matrix, see gp.cu).  alpha = L^-T z is either one streaming pass over T = L^-1 (gemv_t_kernel) or the
-// blocked backward sweep below: one launch per 128-row block; every CTA first recomputes the block's
-// solution with the stored inverse of the diagonal block (128x128 GEMV, L2 resident) and then applies
-// it to its own slice of the remaining right-hand side, so the sweep streams L exactly once.
+// two-level backward sweep of launch_trsv_backward: per 1024-row panel one cluster launch for the chain of 128-row
+// block solves (trsv_bwd_chain_kernel) and single-owner streaming updates of everything left of the panel
+// (trsv_bwd_update_kernel), so the sweep streams L exactly once.  trsv_bwd_step_kernel is the older one-launch-per-block
+// chain (tuning "bwd_cluster" = 0), kept as the reference the cluster kernel is tested against.
 // ------------------------------------------------------------------------------------------------
 constexpr int TRSV_THREADS = 256;
-constexpr int BWD_COLS = 512;   // columns per CTA of the panel kernel
 constexpr int BWD_STEP_COLS = 128;  // columns per CTA of the step kernel (4 row groups x 64 column pairs)
 
 // One 128-row block of the backward sweep.  The launch is latency bound (a chain of dependent global round
