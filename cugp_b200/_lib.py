@@ -98,6 +98,7 @@ SIGNATURES = {
     "cugp_debug_gemm": (C.c_int, [dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                   C.c_int, C.c_int, dp]),
     "cugp_debug_diag_phases": (C.c_int, [dp, C.POINTER(C.c_longlong), C.c_int]),
+    "cugp_debug_step_stamps": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_float)]),
     "cugp_probe_copy": (C.c_int, [C.c_size_t, C.c_int, dp]),
 }
 

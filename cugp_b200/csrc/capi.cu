@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "capi_internal.h"
+#include "cholstep.cuh"
 #include "gp.cuh"
 #include "optim.h"
 
@@ -124,6 +125,10 @@ int cugp_set_tuning(const char* key, long value) {
     }
     if (std::strcmp(key, "lookahead") == 0) {
         set_lookahead(value != 0);
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "fused_step") == 0) {
+        set_fused_step(value != 0);
         return CUGP_OK;
     }
     if (std::strcmp(key, "bwd_cluster") == 0) {
@@ -516,7 +521,7 @@ int cugp_tri_solve_matrix(const double* Tri, const double* Bm, double* X, int n,
     g.ensure_TW();
     const int64_t sI = (int64_t)g.nblk * kDiag * kDiag;
     launch_trtri_diag(g.Kb, g.ld, g.mat_stride(), n, g.invd, sI, 1, g.st);
-    g.launches += g.nblk;
+    g.launches++;
     CUGP_CUDA(cudaMemsetAsync(g.Tb, 0, (size_t)n * g.ld * 8, g.st));
     trtri_recursive(g.Kb, g.Tb, g.Wb, g.ld, g.mat_stride(), n, g.invd, sI, 1, g.st, &g.launches);
     // B into Kb (L is no longer needed), X into Wb
@@ -817,6 +822,27 @@ int cugp_debug_diag_phases(const double* A128, long long* stamps, int nstamps) {
     for (int i = 0; i < nstamps && i < 32; i++) stamps[i] = h[i];
     cudaFree(dA); cudaFree(dInv); cudaFree(dLd); cudaFree(dS);
     return CUGP_OK;
+    CUGP_CATCH
+}
+// Phase stamps of the fused Cholesky block steps of ONE factorisation of a resident Covsum (tools/r2_step_phases.py):
+// stamps[nblk][3 roles][16] globaltimer ns; returns the device time of the factorisation.
+int cugp_debug_step_stamps(cugp_covsum* h, long long* stamps, int nblk_cap, float* ms_chol) {
+    CUGP_TRY
+    if (!h || !stamps || !h->gp->have_data) return CUGP_ERR_INVALID;
+    GpBatch& g = *h->gp;
+    if (nblk_cap < g.nblk) return CUGP_ERR_INVALID;
+    long long* d = nullptr;
+    const size_t cnt = (size_t)g.nblk * 48;
+    CUGP_CUDA(cudaMalloc((void**)&d, cnt * 8));
+    CUGP_CUDA(cudaMemset(d, 0, cnt * 8));
+    set_step_stamps(d);
+    float a = 0, b = 0;
+    int rc = cugp_covsum_factorize_resident(h, &a, &b);
+    set_step_stamps(nullptr);
+    if (ms_chol) *ms_chol = b;
+    CUGP_CUDA(cudaMemcpy(stamps, d, cnt * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return rc;
     CUGP_CATCH
 }
 int cugp_probe_copy(size_t bytes, int iters, double* gbs) {

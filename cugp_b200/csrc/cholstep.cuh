@@ -1,0 +1,18 @@
+// cholstep.cuh -- fused 128-column block step of the blocked Cholesky (see cholstep.cu).
+#pragma once
+#include "common.cuh"
+
+namespace cugp {
+
+// One launch = SYRK prologue of the diagonal block (if `prologue`) + 128x128 POTRF with its four 32x32 diagonal
+// inverses + (prologue and) TRSM of every 32-row tile below, rows [.., nrows) (nrows > n: appended right-hand sides).
+// `sync`: int[batch][nblk][4], zeroed before the first step of a factorisation.  With `prologue` the block column
+// j0 - 128 must be final and must NOT have been applied to block column j0 yet (the launch applies it).
+// The off-diagonal 32x32 blocks of invd are NOT written: launch_trtri_diag_all() completes them afterwards.
+void launch_chol_step(double* A, int64_t ld, int64_t sA, int n, int nrows, int j0, double* invd, int64_t sInvd,
+                      double* logdet_part, int nblk, int* sync, int prologue, int batch, cudaStream_t st);
+
+// Tuning aid: device buffer [nblk][3][16] of globaltimer stamps written by every step (nullptr: off).
+void set_step_stamps(long long* dev);
+
+}  // namespace cugp

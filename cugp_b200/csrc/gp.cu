@@ -1,5 +1,6 @@
 // gp.cu -- orchestration of the GP hot path on one GPU (see gp.cuh).
 #include "gp.cuh"
+#include "cholstep.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -60,6 +61,10 @@ void set_overlap_inverse(int max_n, int cap) {
 static int g_lookahead = 1;
 void set_lookahead(int v) { g_lookahead = v; bump_tuning_epoch(); }
 bool lookahead_enabled() { return g_lookahead != 0; }
+// Fused block step (cholstep.cu): one launch per 128 columns instead of diag kernel + TRSM GEMM + next-block update GEMM.
+// Used whenever the outer width is 128 (the latency-bound regime).  0 restores round 1's launch chain (A/B runs, tests).
+static int g_fused_step = 1;
+void set_fused_step(int v) { g_fused_step = v; bump_tuning_epoch(); }
 static int g_potrf_nb = 0;  // 0: by size; otherwise forced (cugp_set_tuning("potrf_nb", v) or CUGP_POTRF_NB)
 void set_potrf_outer_width(int nb) { g_potrf_nb = nb; bump_tuning_epoch(); }
 int potrf_outer_width(int n) {
@@ -141,14 +146,66 @@ static void potrf_trailing(double* A, int64_t ld, int64_t sA, int nrows, int J0,
     if (launches) ++*launches;
 }
 
+// Outer width 128 with the fused step kernel.  Block column J is final after step(J); step(J) itself applies block
+// column J-1 to block column J (its prologue), so the trailing update of panel J only covers the columns right of
+// block J+1 -- U2(J) -- and, with look-ahead, runs on the main stream while the panel stream is already at step(J+1).
+// Both step(J+2) and U2(J) touch block column J+2: step(J+2) waits for U2(J).
+static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, double* invd, int64_t sInvd, double* logdet_part,
+                        int nblk, int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la,
+                        int* stepsync) {
+    CUGP_CUDA(cudaMemsetAsync(stepsync, 0, (size_t)batch * nblk * 4 * sizeof(int), st));
+    const bool ahead = la && la->st2 && nblk >= 3 && lookahead_enabled();
+    if (!ahead) {
+        for (int J = 0; J < nblk; J++) {
+            const int J0 = J * kDiag, Jend = std::min(n, J0 + kDiag), Jend2 = std::min(n, Jend + kDiag);
+            launch_chol_step(A, ld, sA, n, nrows, J0, invd, sInvd, logdet_part, nblk, stepsync, J > 0, batch, st);
+            if (launches) ++*launches;
+            potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend2, n, batch, st, launches, prof);
+        }
+        launch_trtri_diag(A, ld, sA, n, invd, sInvd, batch, st);
+        if (launches) ++*launches;
+        return;
+    }
+    cudaStream_t s2 = la->st2;
+    while ((int)la->ev.size() < 2 * nblk + 2) {
+        cudaEvent_t e;
+        CUGP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        la->ev.push_back(e);
+    }
+    auto evP = [&](int J) { return la->ev[2 * J]; };
+    auto evU = [&](int J) { return la->ev[2 * J + 1]; };
+    cudaEvent_t ev_start = la->ev[2 * nblk], ev_end = la->ev[2 * nblk + 1];
+    CUGP_CUDA(cudaEventRecord(ev_start, st));
+    CUGP_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
+    for (int J = 0; J < nblk; J++) {
+        const int J0 = J * kDiag, Jend = std::min(n, J0 + kDiag), Jend2 = std::min(n, Jend + kDiag);
+        if (J >= 2) CUGP_CUDA(cudaStreamWaitEvent(s2, evU(J - 2), 0));
+        launch_chol_step(A, ld, sA, n, nrows, J0, invd, sInvd, logdet_part, nblk, stepsync, J > 0, batch, s2);
+        if (launches) ++*launches;
+        if (Jend2 >= n) continue;   // nothing right of block J+1
+        CUGP_CUDA(cudaEventRecord(evP(J), s2));
+        CUGP_CUDA(cudaStreamWaitEvent(st, evP(J), 0));
+        potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend2, n, batch, st, launches, prof);   // U2(J)
+        CUGP_CUDA(cudaEventRecord(evU(J), st));
+    }
+    launch_trtri_diag(A, ld, sA, n, invd, sInvd, batch, s2);   // off-diagonal 32x32 blocks of the 128x128 inverses
+    if (launches) ++*launches;
+    CUGP_CUDA(cudaEventRecord(ev_end, s2));
+    CUGP_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
+}
+
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part, int batch,
-                   cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la, int rhs_rows) {
+                   cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la, int rhs_rows, int* stepsync) {
     if (prof && !prof->on) prof = nullptr;
     const int nrows = n + rhs_rows;
     const int nblk = cdiv(n, kDiag);
     const int NB = potrf_outer_width(n);
     const int npanels = cdiv(n, NB);
     if (la) la->panel_events = false;
+    if (stepsync && g_fused_step && NB == kDiag) {
+        potrf_fused(A, ld, sA, n, nrows, invd, sInvd, logdet_part, nblk, batch, st, launches, prof, la, stepsync);
+        return;
+    }
     if (!la || !la->st2 || npanels < 3 || !lookahead_enabled()) {
         for (int J0 = 0; J0 < n; J0 += NB) {
             const int Jend = std::min(n, J0 + NB);
@@ -275,12 +332,13 @@ GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(
     dalloc(scal, (size_t)B * 4);
     dalloc(tpart, trsv_backward_scratch(n, B));
     dalloc(gradout, (size_t)B * 3);
+    dalloc(stepsync, (size_t)B * nblk * 4);
 }
 
 GpBatch::~GpBatch() {
     if (st) cudaStreamSynchronize(st);
     dfree(X); dfree(y); dfree(Kb); dfree(invd); dfree(logdet_part); dfree(work); dfree(alpha); dfree(scal);
-    dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout); dfree(tpart);
+    dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout); dfree(tpart); dfree(stepsync);
     dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar);
     if (hstage) cudaFreeHost(hstage);
     if (hres) cudaFreeHost(hres);
@@ -432,7 +490,7 @@ void GpBatch::build_K(int full) {
 void GpBatch::potrf(bool with_rhs) {
     auto body = [&] {
         potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la,
-                      with_rhs ? 1 : 0);
+                      with_rhs ? 1 : 0, stepsync);
     };
     if (with_rhs || !run_graphed(graph_potrf, body)) body();   // graph_potrf holds the rhs-free sequence only
 }
@@ -442,7 +500,8 @@ void GpBatch::potrf(bool with_rhs) {
 void GpBatch::potrf_with_rhs() {
     auto body = [&] {
         launch_copy_rows(y, n, Kb + (int64_t)n * ld, mat_stride(), n, B, st);
-        potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la, 1);
+        potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la, 1,
+                      stepsync);
         const double* zrow = Kb + (int64_t)n * ld;
         launch_ll_finalize(zrow, zrow, mat_stride(), n, logdet_part, nblk, scal, B, st);
         launches += 2;

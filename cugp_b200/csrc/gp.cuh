@@ -36,6 +36,7 @@ struct GpBatch {
     double *Tb = nullptr, *Wb = nullptr;    // [B][n][ld] lazily: T = L^-1 ; scratch, then Kinv (lower)
     double *gradpart = nullptr, *gradout = nullptr;
     double* tpart = nullptr;                // [B][8][n] partial sums of the backward sweep's panel launches
+    int* stepsync = nullptr;                // [B][nblk][4] tickets / flags of the fused Cholesky block steps (cholstep.cu)
     // prediction workspace (lazily sized)
     double *Xt = nullptr, *Ks = nullptr, *meanpart = nullptr, *css = nullptr, *pmean = nullptr, *pvar = nullptr;
     int pred_cap = 0;
@@ -129,7 +130,8 @@ struct GpBatch {
 // 128x128 diagonal blocks and per-block log-determinant partials as by-products.
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part,
                    int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr, PotrfLookahead* la = nullptr,
-                   int rhs_rows = 0);
+                   int rhs_rows = 0, int* stepsync = nullptr);
+void set_fused_step(int v); // 1 (default): one fused launch per 128-column block step when the outer width is 128
 // Tuning epoch: bumped by every tuning change so cached graphs are re-captured.  graph_max_n: largest n whose launch
 // chains are replayed as CUDA graphs (0 disables).
 long tuning_epoch();

@@ -392,6 +392,11 @@ __device__ __forceinline__ void cta_gemm8(int mb, int nbk, bool lower, FA A, FB 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
     potrf_diag_blocked_kernel(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd,
                               double* logdet_part, int nblk, int blk, int factor, long long* prof) {
+    if (blk < 0) {   // one launch over every diagonal block: blockIdx.y selects it
+        blk = blockIdx.y;
+        j0 = blk * kDiag;
+        invd += (int64_t)blk * kDiag * kDiag;
+    }
     extern __shared__ __align__(16) double S[];
     double* tmp = S + DB * DLD;                // [64][TLD]
     double* rdiag = tmp + 64 * TLD;            // [128] reciprocals of L's diagonal
@@ -1067,9 +1072,9 @@ void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* i
         CUGP_CUDA(cudaFuncSetAttribute(potrf_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    for (int blk = 0; blk * DB < n; blk++)
-        potrf_diag_blocked_kernel<<<batch, DIAG_THREADS, smem, st>>>(const_cast<double*>(L), ld, sL, n, blk * DB,
-                                                                     invd + (int64_t)blk * DB * DB, sInvd, nullptr, 0, blk, 0, nullptr);
+    // one launch, blockIdx.y = diagonal block
+    potrf_diag_blocked_kernel<<<dim3(batch, cdiv(n, DB)), DIAG_THREADS, smem, st>>>(const_cast<double*>(L), ld, sL, n, 0, invd,
+                                                                                     sInvd, nullptr, 0, -1, 0, nullptr);
     CUGP_CUDA(cudaGetLastError());
 }
 

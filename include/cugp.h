@@ -223,6 +223,12 @@ int cugp_debug_gemm(const double *A, const double *B, double *C, int M, int N, i
  * (stamps[0] start, [1] loaded, [2..10] (chol, trsm, syrk) per 32-column panel, [11..12] diagonal inverses,
  * [13..14] inverse doubling levels, [15] written back); nstamps >= 20. */
 int cugp_debug_diag_phases(const double *A128, long long *stamps, int nstamps);
+/* Tuning aid: globaltimer (ns) stamps of the fused Cholesky block steps (csrc/cholstep.cu) of one factorisation of the
+ * resident data: stamps[nblk][3][16] -- role 0 = first SYRK-prologue CTA (start, loaded, done), role 1 = diagonal CTA
+ * (start, prologue seen, loaded, then (panel factored, look-ahead part done) x 4, [11] flag released, [12] end),
+ * role 2 = first row tile (start, prologue loaded, prologue done, flag seen, L11 loaded, TRSM done, written).
+ * nblk_cap >= ceil(n/128); ms_chol receives the device time of the factorisation. */
+int cugp_debug_step_stamps(cugp_covsum *h, long long *stamps, int nblk_cap, float *ms_chol);
 /* device copy bandwidth (read + write bytes / s) over `bytes` bytes, GB/s */
 int cugp_probe_copy(size_t bytes, int iters, double *gbs);
 

@@ -44,3 +44,7 @@ np.savez_compressed(f"{OUT}/data_si24000.npz", X=Xa, y=ya, Xtest=Xp[:16], ytest=
 for f in sorted(os.listdir(OUT)):
     if f.endswith(".npz"):
         print(f, os.path.getsize(f"{OUT}/{f}"))
+
+# C4 at 600 test points: rows 0..599 of siproper_10000_10 (the C4 test set is that file)
+np.savez_compressed(f"{OUT}/data_c4_xtest600.npz", Xtest=Xp[:600], ytest=yp[:600])
+print("data_c4_xtest600.npz", os.path.getsize(f"{OUT}/data_c4_xtest600.npz"))

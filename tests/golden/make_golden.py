@@ -7,6 +7,9 @@ Run in the build container (needs /root/reference to have built oracle/_ref):
     python tests/golden/make_golden.py --group c4        # ~7 min   BCM N=24000 K=16
     python tests/golden/make_golden.py --group c2        # ~30 min  n=4096 theta_B
     python tests/golden/make_golden.py --group logs      # instant  known answers from the reference's run logs
+    python tests/golden/make_golden.py --group c2a       # ~45 min  n=4096 theta_A (the start point of serial_gp.cpp:49)
+    python tests/golden/make_golden.py --group c4pred    # ~15 min  BCM N=24000 K=16, 600 test points
+    python tests/golden/make_golden.py --group kinv      # ~3 min   compute_K_inverse at n=1000 and n=2048 (sampled)
 
 Every number is produced by the reference's own compiled code (Covsum / BCM / matrixops) through
 oracle/ref_shim.cpp; nothing here comes from the CUDA product or from the C restatement.
@@ -121,6 +124,49 @@ def group_c2(ref):
     return [covsum_case(ref, "C2_sine4096_thB_pred16", X[:4096], y[:4096], TH_B, X[4096:4112], y[4096:4112])]
 
 
+def group_c2a(ref):
+    """C2's own start point: theta_A on the first 4096 rows (serial_gp.cpp:49; LL in SURVEY App. B)."""
+    d = np.load(f"{HERE}/data_sine4096.npz")
+    X, y = d["X"], d["y"]
+    return [covsum_case(ref, "C2_sine4096_thA_pred16", X[:4096], y[:4096], TH_A, X[4096:4112], y[4096:4112])]
+
+
+def group_c4pred(ref):
+    """C4 ensemble at 600 test points (rows 0..599 of the C3 set): several row tiles of the variance
+    GEMM's column-sum epilogue and, with a small chunk cap, several test-set chunks."""
+    d = np.load(f"{HERE}/data_si24000.npz")
+    Xt = np.load(f"{HERE}/data_c4_xtest600.npz")["Xtest"]
+    t0 = time.time()
+    mu, var = ref.bcm_predict(d["X"], d["y"], 16, TH_C, Xt)
+    c = {"name": "C4_si24000_bcm16_thC_pred600", "kind": "bcm_pred", "n": 24000, "d": 10, "K": 16, "theta": L(TH_C),
+         "m": 600, "mean": L(mu), "var": L(var), "seconds": round(time.time() - t0, 2)}
+    # one expert alone at the same points (Covsum::compute_test_means_and_variances, m = 600)
+    mu1, var1 = ref.predict(d["X"][:1500], d["y"][:1500], TH_B, Xt)
+    c1 = {"name": "C4_expert0_n1500_thB_pred600", "kind": "covsum_pred", "n": 1500, "d": 10, "theta": L(TH_B), "m": 600,
+          "mean": L(mu1), "var": L(var1)}
+    return [c, c1]
+
+
+def group_kinv(ref):
+    """compute_K_inverse (matrixops.cpp:383-435) at n = 1000 and 2048 on the C2 data: every 37th row and column of the
+    inverse, its diagonal and its Frobenius norm (the full matrices would be 8 and 33 MB)."""
+    d = np.load(f"{HERE}/data_sine4096.npz")
+    out = []
+    for n, th in ((1000, TH_B), (2048, TH_B)):
+        X = d["X"][:n]
+        t0 = time.time()
+        K = ref.K_train(X, th)
+        Ki = ref.k_inverse(K)
+        Lm = ref.cholesky(K)
+        idx = list(range(0, n, 37))
+        out.append({"name": f"kinv_sine{n}_thB", "kind": "kinv", "n": n, "d": 10, "theta": L(th), "stride": 37,
+                    "Kinv_sample": L(Ki[np.ix_(idx, idx)]), "Kinv_diag": L(np.diag(Ki)), "Kinv_fro": float(np.linalg.norm(Ki)),
+                    "L_sample": L(Lm[np.ix_(idx, idx)]), "L_fro": float(np.linalg.norm(Lm)),
+                    "seconds": round(time.time() - t0, 2)})
+        print(f"  kinv n={n}: fro={out[-1]['Kinv_fro']!r} ({out[-1]['seconds']} s)", flush=True)
+    return out
+
+
 def group_logs(_ref):
     """Known answers the reference itself ships: 6-digit run logs."""
     log = open("/root/reference/cuda_bettersinglenode_ver2/REF").read()
@@ -142,7 +188,7 @@ def group_logs(_ref):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--group", default="small", choices=["small", "c4", "c2", "logs"])
+    ap.add_argument("--group", default="small", choices=["small", "c4", "c2", "logs", "c2a", "c4pred", "kinv"])
     a = ap.parse_args()
     ref = oracle.reference()
     if ref is None:
@@ -150,7 +196,8 @@ if __name__ == "__main__":
     path = f"{HERE}/golden_{a.group}.json"   # one file per group, so groups can be generated in parallel
     gold = {"generator": f"tests/golden/make_golden.py --group {a.group}",
             "source": "oracle/_ref (unmodified reference objects)", "cases": {}}
-    for c in {"small": group_small, "c4": group_c4, "c2": group_c2, "logs": group_logs}[a.group](ref):
+    for c in {"small": group_small, "c4": group_c4, "c2": group_c2, "logs": group_logs, "c2a": group_c2a,
+              "c4pred": group_c4pred, "kinv": group_kinv}[a.group](ref):
         gold["cases"][c["name"]] = c
     json.dump(gold, open(path, "w"), indent=1)
     print("wrote", path, "with", len(gold["cases"]), "cases")
