@@ -79,6 +79,12 @@ SIGNATURES = {
     "cugp_poe_finalize_dev": (C.c_int, [C.c_void_p, C.c_int, dp, dp]),
     "cugp_poe_finalize": (C.c_int, [dp, C.c_int, dp, dp]),
     "cugp_bcm_predict": (C.c_int, [C.c_void_p, dp, C.c_int, dp, dp]),
+    "cugp_nccl_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
+    "cugp_bcm_comm_init": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte)]),
+    "cugp_bcm_comm_init_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "cugp_bcm_has_comm": (C.c_int, [C.c_void_p]),
+    "cugp_bcm_collectives": (C.c_long, [C.c_void_p]),
+    "cugp_bcm_loglik_grad": (C.c_int, [C.c_void_p, C.c_int, dp]),
     "cugp_shardstream_open_files": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_size_t, C.POINTER(C.c_void_p)]),
     "cugp_shardstream_open_memory": (C.c_int, [dp, dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -9,8 +9,11 @@ resident; each operation has exactly ONE exchange step:
 * training evaluation: allreduce(sum, f64, 4)  of (LL, g0, g1, g2)
 * prediction:          allreduce(sum, f64, 2m) of (sum_e 1/var_e, sum_e mean_e/var_e)
 
-over ``torch.distributed`` (NCCL on GPUs; gloo in the CPU tests of the host logic).  The reference moved the
-same payloads over blocking TCP sockets (cuda_src/cg_solver.cpp:22-79).
+On GPUs the exchange runs INSIDE libcugp: the library owns an NCCL communicator (``cugp_bcm_comm_init``; torch.distributed
+only broadcasts the 128-byte unique id once) and enqueues ``ncclAllReduce`` on its own stream right behind the kernels
+that produce the payload -- no host round trip, no torch tensor.  The gloo path (CPU tests of the host logic) and a
+process group without NCCL go through ``torch.distributed``.  The reference moved the same payloads over blocking TCP
+sockets (cuda_src/cg_solver.cpp:22-79).
 """
 from __future__ import annotations
 
@@ -38,18 +41,41 @@ def local_experts(K: int, rank: int, world: int):
     return list(range(rank, K, world))
 
 
-class _CudaLocal:
-    """This rank's experts on its GPU, through the C ABI."""
+NCCL_ID_BYTES = 128
 
-    def __init__(self, X, y, K, rank, world):
+
+class _CudaLocal:
+    """This rank's experts on its GPU, through the C ABI.  With a communicator (``comm_init``) the exchange step of
+    every operation runs inside the library: ``ncclAllReduce`` on the library's stream, no host round trip."""
+
+    def __init__(self, X, y, K, rank, world, device=None):
         self._h = C.c_void_p()
         N, D = X.shape
+        if device is not None:
+            check(lib().cugp_set_device(int(device)))
         check(lib().cugp_bcm_create(ptr(X), ptr(y), N, D, K, rank, world, C.byref(self._h)))
 
     def close(self):
         if self._h.value:
             lib().cugp_bcm_destroy(self._h)
             self._h = C.c_void_p()
+
+    # -- communicator ------------------------------------------------------------------------------------------
+    @staticmethod
+    def new_unique_id() -> bytes:
+        buf = (C.c_ubyte * NCCL_ID_BYTES)()
+        check(lib().cugp_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes):
+        buf = (C.c_ubyte * NCCL_ID_BYTES).from_buffer_copy(unique_id)
+        check(lib().cugp_bcm_comm_init(self._h, buf))
+
+    def has_comm(self) -> bool:
+        return bool(lib().cugp_bcm_has_comm(self._h))
+
+    def collectives(self) -> int:
+        return int(lib().cugp_bcm_collectives(self._h))
 
     def set_theta(self, th):
         check(lib().cugp_bcm_set_loghyper(self._h, ptr(th)))
@@ -58,6 +84,19 @@ class _CudaLocal:
         out = np.zeros(4)
         check(lib().cugp_bcm_loglik_grad_local(self._h, int(want_grad), ptr(out)))
         return out
+
+    def loglik_grad_all(self, want_grad: bool):
+        """(LL, g) over ALL experts: local sums + the library's own allreduce (collective)."""
+        out = np.zeros(4)
+        check(lib().cugp_bcm_loglik_grad(self._h, int(want_grad), ptr(out)))
+        return out
+
+    def predict_all(self, Xt):
+        """PoE mean / variance over ALL experts: moments + allreduce + finalisation inside the library (collective)."""
+        m = Xt.shape[0]
+        mean, var = np.empty(m), np.empty(m)
+        check(lib().cugp_bcm_predict(self._h, ptr(Xt), m, ptr(mean), ptr(var)))
+        return mean, var
 
     def expert_logliks(self):
         cnt = C.c_int()
@@ -81,7 +120,7 @@ class BCM:
     """``BCM(X, y, N, D, K)`` of the reference; ``group`` is a ``torch.distributed`` process group (or the
     default group when ``torch.distributed`` is initialised), ``None`` for a single process."""
 
-    def __init__(self, X, y, N=None, D=None, K=1, rank=None, world=None, group=None, local_impl=None):
+    def __init__(self, X, y, N=None, D=None, K=1, rank=None, world=None, group=None, local_impl=None, device=None):
         X, y = f64(X), f64(y)
         N = X.shape[0] if N is None else int(N)
         D = X.shape[1] if D is None else int(D)
@@ -104,8 +143,40 @@ class BCM:
         self.rank, self.world, self.group = int(rank), int(world), group
         self.offset = [o for o, _ in expert_partition(N, self.num_experts)]
         self.log_hyper_bcm = np.zeros(3)
-        self._local = (local_impl or _CudaLocal)(X, y, self.num_experts, self.rank, self.world)
-        self.exchanges = 0  # collectives issued (one per operation)
+        self._in_library = False      # the exchange step runs inside libcugp (ncclAllReduce on its own stream)
+        if local_impl is None:
+            # one process per GPU: a rank of an initialised torchrun job drives GPU LOCAL_RANK unless told otherwise;
+            # everything else (a single process, ranks emulated in one process) keeps the current device
+            if device is None and self.world > 1 and self._dist is not None and self._dist.is_initialized():
+                import os
+                if "LOCAL_RANK" in os.environ:
+                    device = int(os.environ["LOCAL_RANK"])
+            self.device = device
+            self._local = _CudaLocal(X, y, self.num_experts, self.rank, self.world, device)
+            if self.world > 1 and self._dist is not None and self._dist.is_initialized() \
+                    and self._dist.get_backend(self.group) == "nccl":
+                # the library builds its OWN communicator; torch.distributed only carries the 128-byte id once
+                box = [_CudaLocal.new_unique_id() if self.rank == 0 else None]
+                src = self._dist.get_global_rank(self.group, 0) if self.group is not None else 0
+                self._dist.broadcast_object_list(box, src=src, group=self.group)
+                self._local.comm_init(box[0])
+                self._in_library = True
+        else:
+            self.device = device
+            self._local = local_impl(X, y, self.num_experts, self.rank, self.world)
+        self._exchanges = 0  # collectives issued through torch.distributed (one per operation)
+
+    @property
+    def exchanges(self):
+        """Collectives issued so far: one per operation, whichever layer carries them."""
+        n = self._exchanges
+        if self._in_library:
+            n += self._local.collectives()
+        return n
+
+    @exchanges.setter
+    def exchanges(self, v):
+        self._exchanges = v
 
     def close(self):
         if getattr(self, "_local", None) is not None and hasattr(self._local, "close"):
@@ -120,7 +191,7 @@ class BCM:
             return arr
         import torch
         dist = self._dist
-        self.exchanges += 1
+        self._exchanges += 1
         backend = dist.get_backend(self.group)
         t = torch.from_numpy(np.ascontiguousarray(arr))
         if backend == "nccl":
@@ -147,10 +218,15 @@ class BCM:
     # -- training evaluation (BCM.cpp:153-198) ---------------------------------------------------------------------
     def loglik_and_gradient(self):
         """One factorisation per expert, one allreduce of 4 doubles: (LL, grad[3])."""
-        out = self._allreduce(self._local.loglik_grad(True))
+        if self._in_library:
+            out = self._local.loglik_grad_all(True)
+        else:
+            out = self._allreduce(self._local.loglik_grad(True))
         return float(out[0]), out[1:4].copy()
 
     def get_BCM_loglikelihood(self):
+        if self._in_library:
+            return float(self._local.loglik_grad_all(False)[0])
         return float(self._allreduce(self._local.loglik_grad(False))[0])
 
     def get_BCM_gradient_hyper(self):
@@ -162,13 +238,15 @@ class BCM:
         m = Xt.shape[0]
         if m == 0:
             return np.empty(0), np.empty(0)
+        if self._in_library or (self.world == 1 and hasattr(self._local, "predict_all")):
+            return self._local.predict_all(Xt)
         nccl = self.world > 1 and self._dist is not None and self._dist.get_backend(self.group) == "nccl"
         if nccl and hasattr(self._local, "moments_into"):
             # device-resident exchange: the moments never leave HBM before the NCCL allreduce
             import torch
             PQ = torch.empty(2 * m, dtype=torch.float64, device="cuda")
             self._local.moments_into(Xt, PQ.data_ptr())
-            self.exchanges += 1
+            self._exchanges += 1
             self._dist.all_reduce(PQ, op=self._dist.ReduceOp.SUM, group=self.group)
             torch.cuda.current_stream().synchronize()
             mean, var = np.empty(m), np.empty(m)

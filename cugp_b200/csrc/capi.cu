@@ -2,12 +2,19 @@
 // needs a CUDA device and the sm_100a kernels in this library.
 #include "../../include/cugp.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "capi_internal.h"
@@ -57,8 +64,16 @@ static std::vector<GpBatch*>& live_batches() {
     static std::vector<GpBatch*> v;
     return v;
 }
-void track(GpBatch* g) { live_batches().push_back(g); }
+static std::mutex& track_mutex() {
+    static std::mutex m;
+    return m;
+}
+void track(GpBatch* g) {
+    std::lock_guard<std::mutex> lock(track_mutex());
+    live_batches().push_back(g);
+}
 void untrack(GpBatch* g) {
+    std::lock_guard<std::mutex> lock(track_mutex());
     auto& v = live_batches();
     g_launch_base += g->launches;
     v.erase(std::remove(v.begin(), v.end(), g), v.end());
@@ -104,11 +119,13 @@ int cugp_set_device(int device) {
     CUGP_CATCH
 }
 long cugp_launch_count(void) {
+    std::lock_guard<std::mutex> lock(track_mutex());
     long s = g_launch_base;
     for (GpBatch* g : live_batches()) s += g->launches;
     return s;
 }
 void cugp_launch_count_reset(void) {
+    std::lock_guard<std::mutex> lock(track_mutex());
     g_launch_base = 0;
     for (GpBatch* g : live_batches()) g->launches = 0;
 }
@@ -125,6 +142,11 @@ int cugp_set_tuning(const char* key, long value) {
     }
     if (std::strcmp(key, "lookahead") == 0) {
         set_lookahead(value != 0);
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "pred_chunk") == 0) {
+        if (value < 0) return CUGP_ERR_INVALID;
+        set_pred_chunk((int)value);
         return CUGP_OK;
     }
     if (std::strcmp(key, "fused_step") == 0) {
@@ -546,8 +568,66 @@ int cugp_tri_solve_matrix(const double* Tri, const double* Bm, double* X, int n,
 }  // extern "C"
 
 // ---- BCM --------------------------------------------------------------------------------------------
+// NCCL is bound at run time (dlopen of libnccl.so.2: the copy the process already holds -- torch's -- or the system
+// one), so the library has no link-time dependency on it and loads on boxes without NCCL; only the multi-GPU
+// entry points need it.
+namespace {
+struct NcclApi {
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+    const char* why = "";
+};
+NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) {
+            a.why = "libnccl.so.2 not found";
+            return a;
+        }
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+        a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+        if (!a.ok) a.why = "libnccl.so.2 lacks a required symbol";
+        return a;
+    }();
+    return api;
+}
+struct NcclError {
+    ncclResult_t code;
+    int line;
+};
+#define CUGP_NCCL(expr)                                         \
+    do {                                                        \
+        ncclResult_t _r = (expr);                               \
+        if (_r != ncclSuccess) throw NcclError{_r, __LINE__};   \
+    } while (0)
+
+// sum over the local experts, in expert order, of (LL, g0, g1, g2): scal is [B][4] (LL at [2]), grad [B][3]
+__global__ void bcm_sum4_kernel(const double* scal, const double* grad, int B, int want_grad, double* out4, int accumulate) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    if (accumulate)
+        for (int k = 0; k < 4; k++) s[k] = out4[k];
+    for (int b = 0; b < B; b++) {
+        s[0] += scal[b * 4 + 2];
+        if (want_grad)
+            for (int k = 0; k < 3; k++) s[1 + k] += grad[b * 3 + k];
+    }
+    for (int k = 0; k < 4; k++) out4[k] = s[k];
+}
+}  // namespace
+
 struct cugp_bcm {
-    int N, D, K, rank, world;
+    int N, D, K, rank, world, device = 0;
     double theta[3] = {0, 0, 0};
     struct Group {
         std::unique_ptr<GpBatch> gp;
@@ -555,29 +635,116 @@ struct cugp_bcm {
     };
     std::vector<Group> groups;   // at most two: the floor(N/K)-row experts and the remainder expert
     std::vector<int> local_ids;  // ascending
-    double* PQ = nullptr;        // device [2][m] scratch for the host-buffer variants
+    double* PQ = nullptr;        // device [2][m] moments, then [2][m] finalised (mean, var) behind them
     int pq_cap = 0;
+    double* hfin = nullptr;      // pinned [2][m] host landing buffer of a prediction
+    int hfin_cap = 0;
+    double* red4 = nullptr;      // device [4]: (LL, g) summed over the local experts, allreduced in place
+    double* hred4 = nullptr;     // pinned [4]
+    double* Xt_dev = nullptr;    // replicated test set on the device, [m][dp]; re-uploaded only when it changes
+    std::vector<double> Xt_host;
+    int xt_m = 0, xt_cap = 0;
     cudaStream_t st = nullptr;
+    ncclComm_t comm = nullptr;
+    long collectives = 0;
     ~cugp_bcm() {
+        if (st) cudaStreamSynchronize(st);
+        if (comm && nccl_api().ok) nccl_api().CommDestroy(comm);
         for (auto& g : groups) untrack(g.gp.get());
         groups.clear();
         if (PQ) cudaFree(PQ);
+        if (red4) cudaFree(red4);
+        if (Xt_dev) cudaFree(Xt_dev);
+        if (hfin) cudaFreeHost(hfin);
+        if (hred4) cudaFreeHost(hred4);
         if (st) cudaStreamDestroy(st);
     }
 };
 
+// every entry point runs on the device the handle was created on (one process may hold handles on several GPUs)
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static void ensure_pq(cugp_bcm* h, int m) {
+    if (m > h->pq_cap) {
+        CUGP_CUDA(cudaStreamSynchronize(h->st));
+        if (h->PQ) cudaFree(h->PQ);
+        h->PQ = nullptr;
+        CUGP_CUDA(cudaMalloc((void**)&h->PQ, (size_t)4 * m * 8));
+        h->pq_cap = m;
+    }
+    if (m > h->hfin_cap) {
+        CUGP_CUDA(cudaStreamSynchronize(h->st));
+        if (h->hfin) cudaFreeHost(h->hfin);
+        h->hfin = nullptr;
+        CUGP_CUDA(cudaMallocHost((void**)&h->hfin, (size_t)2 * m * 8));
+        h->hfin_cap = m;
+    }
+}
+
+// The replicated test set: packed to the padded layout and uploaded only when its bytes differ from the last call's.
+static const double* bcm_test_points(cugp_bcm* h, const double* Xtest, int m) {
+    const size_t cnt = (size_t)m * h->D;
+    if (h->xt_m == m && h->Xt_host.size() == cnt && std::memcmp(h->Xt_host.data(), Xtest, cnt * 8) == 0) return h->Xt_dev;
+    const int dp = (int)round_up(h->D, 2);
+    if (m > h->xt_cap) {
+        CUGP_CUDA(cudaStreamSynchronize(h->st));
+        if (h->Xt_dev) cudaFree(h->Xt_dev);
+        h->Xt_dev = nullptr;
+        CUGP_CUDA(cudaMalloc((void**)&h->Xt_dev, (size_t)m * dp * 8));
+        h->xt_cap = m;
+    }
+    h->Xt_host.assign(Xtest, Xtest + cnt);
+    h->xt_m = m;
+    CUGP_CUDA(cudaStreamSynchronize(h->st));   // Xt_host's previous contents may still feed a copy
+    if (dp == h->D) {
+        CUGP_CUDA(cudaMemcpyAsync(h->Xt_dev, h->Xt_host.data(), cnt * 8, cudaMemcpyHostToDevice, h->st));
+    } else {
+        CUGP_CUDA(cudaMemsetAsync(h->Xt_dev, 0, (size_t)m * dp * 8, h->st));
+        CUGP_CUDA(cudaMemcpy2DAsync(h->Xt_dev, (size_t)dp * 8, h->Xt_host.data(), (size_t)h->D * 8, (size_t)h->D * 8, (size_t)m,
+                                    cudaMemcpyHostToDevice, h->st));
+    }
+    return h->Xt_dev;
+}
+
+// local product-of-experts moments into PQ_dev ([2][m] device), queued on h->st (all groups share it: ordered)
 static void bcm_moments(cugp_bcm* h, const double* Xtest, int m, double* PQ_dev) {
     if (h->groups.empty()) {
         CUGP_CUDA(cudaMemsetAsync(PQ_dev, 0, (size_t)2 * m * 8, h->st));
-        CUGP_CUDA(cudaStreamSynchronize(h->st));
         return;
     }
+    const double* Xt = bcm_test_points(h, Xtest, m);
     int acc = 0;
     for (auto& g : h->groups) {
-        g.gp->predict(Xtest, m, nullptr, nullptr, PQ_dev, acc);  // all groups share h->st: ordered
+        g.gp->predict_dev(Xt, m, nullptr, nullptr, PQ_dev, acc);
         acc = 1;
     }
 }
+
+static void bcm_allreduce(cugp_bcm* h, double* buf, size_t count) {
+    if (h->world == 1) return;
+    if (!h->comm) throw NcclError{ncclInvalidUsage, __LINE__};
+    CUGP_NCCL(nccl_api().AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->st));
+    h->collectives++;
+}
+
+#define CUGP_CATCH_NCCL                                                                                       \
+    }                                                                                                         \
+    catch (const NcclError& e) {                                                                              \
+        set_last_error("NCCL error %d (%s) at capi.cu:%d%s", (int)e.code,                                     \
+                       nccl_api().ok ? nccl_api().GetErrorString(e.code) : nccl_api().why, e.line,            \
+                       e.code == ncclInvalidUsage ? " -- world > 1 needs cugp_bcm_comm_init first" : "");     \
+        return CUGP_ERR_CUDA;                                                                                 \
+    CUGP_CATCH
 
 extern "C" {
 
@@ -590,7 +757,10 @@ int cugp_bcm_create(const double* X, const double* y, int N, int D, int K, int r
     if (int rc = require_device()) return rc;
     std::unique_ptr<cugp_bcm> h(new cugp_bcm);
     h->N = N; h->D = D; h->K = K; h->rank = rank; h->world = world;
+    CUGP_CUDA(cudaGetDevice(&h->device));
     CUGP_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CUGP_CUDA(cudaMalloc((void**)&h->red4, 4 * 8));
+    CUGP_CUDA(cudaMallocHost((void**)&h->hred4, 4 * 8));
     const int part = N / K, last = N - (K - 1) * part;  // BCM.cpp:92-108
     std::vector<int> uni, rem;
     for (int e = rank; e < K; e += world) {
@@ -627,6 +797,8 @@ int cugp_bcm_dims(cugp_bcm* h, int* N, int* D, int* K) {
     return CUGP_OK;
 }
 int cugp_bcm_destroy(cugp_bcm* h) {
+    if (!h) return CUGP_OK;
+    DeviceGuard dg(h->device);
     delete h;
     return CUGP_OK;
 }
@@ -641,26 +813,124 @@ int cugp_bcm_get_loghyper(cugp_bcm* h, double theta[3]) {
     for (int i = 0; i < 3; i++) theta[i] = h->theta[i];
     return CUGP_OK;
 }
+
+// ---- the exchange step inside the library (replaces the sockets of cuda_src/cg_solver.cpp:22-79) ----------
+int cugp_nccl_unique_id(unsigned char id[CUGP_NCCL_ID_BYTES]) {
+    CUGP_TRY
+    if (!id) return CUGP_ERR_INVALID;
+    static_assert(sizeof(ncclUniqueId) == CUGP_NCCL_ID_BYTES, "ncclUniqueId size");
+    if (!nccl_api().ok) {
+        set_last_error("NCCL unavailable: %s", nccl_api().why);
+        return CUGP_ERR_INVALID;
+    }
+    ncclUniqueId u;
+    CUGP_NCCL(nccl_api().GetUniqueId(&u));
+    std::memcpy(id, &u, sizeof(u));
+    return CUGP_OK;
+    CUGP_CATCH_NCCL
+}
+int cugp_bcm_comm_init(cugp_bcm* h, const unsigned char id[CUGP_NCCL_ID_BYTES]) {
+    CUGP_TRY
+    if (!h || !id) return CUGP_ERR_INVALID;
+    if (h->world == 1) return CUGP_OK;
+    if (!nccl_api().ok) {
+        set_last_error("NCCL unavailable: %s", nccl_api().why);
+        return CUGP_ERR_INVALID;
+    }
+    DeviceGuard dg(h->device);
+    if (h->comm) {
+        nccl_api().CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof(u));
+    CUGP_NCCL(nccl_api().CommInitRank(&h->comm, h->world, u, h->rank));
+    return CUGP_OK;
+    CUGP_CATCH_NCCL
+}
+// Rendezvous through a file for callers without their own broadcast (the C++ shim's BCM): rank 0 creates the id and
+// renames it into place, the others wait for the file.  The path must be fresh for every communicator.
+int cugp_bcm_comm_init_file(cugp_bcm* h, const char* path, int timeout_s) {
+    CUGP_TRY
+    if (!h || !path) return CUGP_ERR_INVALID;
+    if (h->world == 1) return CUGP_OK;
+    unsigned char id[CUGP_NCCL_ID_BYTES];
+    if (h->rank == 0) {
+        if (int rc = cugp_nccl_unique_id(id)) return rc;
+        const std::string tmp = std::string(path) + ".tmp";
+        FILE* f = std::fopen(tmp.c_str(), "wb");
+        if (!f || std::fwrite(id, 1, sizeof(id), f) != sizeof(id)) {
+            if (f) std::fclose(f);
+            set_last_error("cannot write %s", tmp.c_str());
+            return CUGP_ERR_INVALID;
+        }
+        std::fclose(f);
+        if (std::rename(tmp.c_str(), path) != 0) {
+            set_last_error("cannot rename %s", tmp.c_str());
+            return CUGP_ERR_INVALID;
+        }
+    } else {
+        bool got = false;
+        for (int waited_ms = 0; waited_ms <= timeout_s * 1000 && !got; waited_ms += 20) {
+            if (FILE* f = std::fopen(path, "rb")) {
+                got = std::fread(id, 1, sizeof(id), f) == sizeof(id);
+                std::fclose(f);
+            }
+            if (!got) std::this_thread::sleep_for(std::chrono::milliseconds(20));
+        }
+        if (!got) {
+            set_last_error("rank %d: no NCCL id at %s after %d s", h->rank, path, timeout_s);
+            return CUGP_ERR_INVALID;
+        }
+    }
+    return cugp_bcm_comm_init(h, id);
+    CUGP_CATCH
+}
+int cugp_bcm_has_comm(cugp_bcm* h) { return h && h->comm ? 1 : 0; }
+long cugp_bcm_collectives(cugp_bcm* h) { return h ? h->collectives : 0; }
+
+// (LL, g0, g1, g2) summed over this rank's experts: every group's evaluation is queued first, ONE wait at the end.
+static void bcm_eval_enqueue(cugp_bcm* h, int want_grad) {
+    int acc = 0;
+    for (auto& g : h->groups) {  // groups are in ascending expert order, experts ascending inside
+        g.gp->eval_enqueue(want_grad != 0);
+        bcm_sum4_kernel<<<1, 32, 0, h->st>>>(g.gp->scal, g.gp->gradout, g.gp->B, want_grad, h->red4, acc);
+        g.gp->launches++;
+        acc = 1;
+    }
+    if (!acc) CUGP_CUDA(cudaMemsetAsync(h->red4, 0, 4 * 8, h->st));
+    CUGP_CUDA(cudaGetLastError());
+}
+static void bcm_eval_collect(cugp_bcm* h, double out4[4]) {
+    CUGP_CUDA(cudaMemcpyAsync(h->hred4, h->red4, 4 * 8, cudaMemcpyDeviceToHost, h->st));
+    CUGP_CUDA(cudaStreamSynchronize(h->st));
+    for (int k = 0; k < 4; k++) out4[k] = h->hred4[k];
+}
 int cugp_bcm_loglik_grad_local(cugp_bcm* h, int want_grad, double out4[4]) {
     CUGP_TRY
     if (!h || !out4) return CUGP_ERR_INVALID;
-    out4[0] = out4[1] = out4[2] = out4[3] = 0.0;
-    for (auto& g : h->groups) {  // groups are in ascending expert order, experts ascending inside
-        const int B = g.gp->B;
-        std::vector<double> ll(B), gr((size_t)B * 3, 0.0);
-        g.gp->loglik(ll.data());
-        if (want_grad) g.gp->gradient(gr.data());
-        for (int b = 0; b < B; b++) {
-            out4[0] += ll[b];
-            for (int k = 0; k < 3; k++) out4[1 + k] += gr[(size_t)b * 3 + k];
-        }
-    }
+    DeviceGuard dg(h->device);
+    bcm_eval_enqueue(h, want_grad);
+    bcm_eval_collect(h, out4);
     return CUGP_OK;
     CUGP_CATCH
+}
+// The reference's get_BCM_loglikelihood / get_BCM_gradient_hyper (BCM.cpp:153-198) over ALL experts: local sums, then
+// one ncclAllReduce(sum, f64, 4) enqueued on the library stream right behind them, one device->host copy, one wait.
+int cugp_bcm_loglik_grad(cugp_bcm* h, int want_grad, double out4[4]) {
+    CUGP_TRY
+    if (!h || !out4) return CUGP_ERR_INVALID;
+    DeviceGuard dg(h->device);
+    bcm_eval_enqueue(h, want_grad);
+    bcm_allreduce(h, h->red4, 4);
+    bcm_eval_collect(h, out4);
+    return CUGP_OK;
+    CUGP_CATCH_NCCL
 }
 int cugp_bcm_local_experts(cugp_bcm* h, int* count, int* ids, double* ll) {
     CUGP_TRY
     if (!h || !count) return CUGP_ERR_INVALID;
+    DeviceGuard dg(h->device);
     *count = (int)h->local_ids.size();
     size_t k = 0;
     for (auto& g : h->groups) {
@@ -677,48 +947,55 @@ int cugp_bcm_local_experts(cugp_bcm* h, int* count, int* ids, double* ll) {
 int cugp_bcm_predict_moments_dev(cugp_bcm* h, const double* Xtest, int m, double* PQ_dev) {
     CUGP_TRY
     if (!h || !Xtest || m <= 0 || !PQ_dev) return CUGP_ERR_INVALID;
+    DeviceGuard dg(h->device);
     bcm_moments(h, Xtest, m, PQ_dev);
+    CUGP_CUDA(cudaStreamSynchronize(h->st));   // the caller's collective runs on another stream
     return CUGP_OK;
     CUGP_CATCH
-}
-static void ensure_pq(cugp_bcm* h, int m) {
-    if (m <= h->pq_cap) return;
-    if (h->PQ) cudaFree(h->PQ);
-    h->PQ = nullptr;
-    CUGP_CUDA(cudaMalloc((void**)&h->PQ, (size_t)2 * m * 8));
-    h->pq_cap = m;
 }
 int cugp_bcm_predict_moments(cugp_bcm* h, const double* Xtest, int m, double* PQ) {
     CUGP_TRY
     if (!h || !Xtest || m <= 0 || !PQ) return CUGP_ERR_INVALID;
+    DeviceGuard dg(h->device);
     ensure_pq(h, m);
     bcm_moments(h, Xtest, m, h->PQ);
-    CUGP_CUDA(cudaMemcpy(PQ, h->PQ, (size_t)2 * m * 8, cudaMemcpyDeviceToHost));
+    CUGP_CUDA(cudaMemcpyAsync(h->hfin, h->PQ, (size_t)2 * m * 8, cudaMemcpyDeviceToHost, h->st));
+    CUGP_CUDA(cudaStreamSynchronize(h->st));
+    std::memcpy(PQ, h->hfin, (size_t)2 * m * 8);
     return CUGP_OK;
     CUGP_CATCH
 }
+// Finalisation of moments that a caller allreduced itself (device pointer).  Scratch is per device and guarded.
 int cugp_poe_finalize_dev(const double* PQ_dev, int m, double* mean, double* var) {
     CUGP_TRY
     if (!PQ_dev || m <= 0 || !mean || !var) return CUGP_ERR_INVALID;
-    // grow-only scratch (device + pinned host): this call sits behind every multi-GPU prediction's allreduce, and a
-    // cudaMalloc/cudaFree pair per call costs more than the kernel and both copies together
-    static double* out = nullptr;
-    static double* hout = nullptr;
-    static int cap = 0;
-    if (m > cap) {
-        if (out) cudaFree(out);
-        if (hout) cudaFreeHost(hout);
-        out = hout = nullptr;
-        cap = 0;
-        CUGP_CUDA(cudaMalloc((void**)&out, (size_t)2 * m * 8));
-        CUGP_CUDA(cudaMallocHost((void**)&hout, (size_t)2 * m * 8));
-        cap = m;
+    struct Scratch {
+        double *out = nullptr, *hout = nullptr;
+        int cap = 0;
+        cudaStream_t st = nullptr;
+    };
+    static std::mutex mu;
+    static Scratch per_dev[64];
+    int dev = 0;
+    CUGP_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return CUGP_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(mu);
+    Scratch& s = per_dev[dev];
+    if (!s.st) CUGP_CUDA(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    if (m > s.cap) {
+        if (s.out) cudaFree(s.out);
+        if (s.hout) cudaFreeHost(s.hout);
+        s.out = s.hout = nullptr;
+        s.cap = 0;
+        CUGP_CUDA(cudaMalloc((void**)&s.out, (size_t)2 * m * 8));
+        CUGP_CUDA(cudaMallocHost((void**)&s.hout, (size_t)2 * m * 8));
+        s.cap = m;
     }
-    launch_poe_finalize(PQ_dev, m, out, out + m, 0);
-    CUGP_CUDA(cudaMemcpyAsync(hout, out, (size_t)2 * m * 8, cudaMemcpyDeviceToHost, 0));
-    CUGP_CUDA(cudaStreamSynchronize(0));
-    std::memcpy(mean, hout, (size_t)m * 8);
-    std::memcpy(var, hout + m, (size_t)m * 8);
+    launch_poe_finalize(PQ_dev, m, s.out, s.out + m, s.st);
+    CUGP_CUDA(cudaMemcpyAsync(s.hout, s.out, (size_t)2 * m * 8, cudaMemcpyDeviceToHost, s.st));
+    CUGP_CUDA(cudaStreamSynchronize(s.st));
+    std::memcpy(mean, s.hout, (size_t)m * 8);
+    std::memcpy(var, s.hout + m, (size_t)m * 8);
     return CUGP_OK;
     CUGP_CATCH
 }
@@ -731,17 +1008,22 @@ int cugp_poe_finalize(const double* PQ, int m, double* mean, double* var) {
     }
     return CUGP_OK;
 }
+// compute_BCM_test_means_and_var (BCM.cpp:64-83) over ALL experts: local moments, one ncclAllReduce(sum, f64, 2m) and the
+// finalisation kernel on the same stream, one device->host copy, one wait.
 int cugp_bcm_predict(cugp_bcm* h, const double* Xtest, int m, double* mean, double* var) {
     CUGP_TRY
     if (!h || !Xtest || m <= 0 || !mean || !var) return CUGP_ERR_INVALID;
-    if (h->world != 1) {
-        set_last_error("cugp_bcm_predict needs world == 1; use predict_moments + allreduce + poe_finalize");
-        return CUGP_ERR_INVALID;
-    }
+    DeviceGuard dg(h->device);
     ensure_pq(h, m);
     bcm_moments(h, Xtest, m, h->PQ);
-    return cugp_poe_finalize_dev(h->PQ, m, mean, var);
-    CUGP_CATCH
+    bcm_allreduce(h, h->PQ, (size_t)2 * m);
+    launch_poe_finalize(h->PQ, m, h->PQ + 2 * (size_t)m, h->PQ + 3 * (size_t)m, h->st);
+    CUGP_CUDA(cudaMemcpyAsync(h->hfin, h->PQ + 2 * (size_t)m, (size_t)2 * m * 8, cudaMemcpyDeviceToHost, h->st));
+    CUGP_CUDA(cudaStreamSynchronize(h->st));
+    std::memcpy(mean, h->hfin, (size_t)m * 8);
+    std::memcpy(var, h->hfin + m, (size_t)m * 8);
+    return CUGP_OK;
+    CUGP_CATCH_NCCL
 }
 
 // ---- probes -----------------------------------------------------------------------------------------

@@ -109,59 +109,137 @@ __device__ __forceinline__ void blocks_mma(int first, int stride, int count, FBL
 }
 
 // ------------------------------------------------------------------------------------------------
-// 32x32 Cholesky + inverse by ONE warp (matrixops.cpp:74-98 and :330-340 on the sub-block).
-// Lane i owns row i of A -> L (entries c < i) and column i of T = inv(L) (entries c > i) in ONE array u[32]; the
-// diagonal entries live in scalars.  Column j:
-//     rd = rsqrt(a_jj),  L(i,j) = a_ij rd (i > j),  T(j,i) = r_j rd (i < j),  d = a_jj rd = L(j,j),  T(j,j) = rd
-//     cb[] <- column j of L (shared-memory broadcast)
-//     u[c] -= cb[c] * m   for c > j,  m = L(i,j) for lanes below the pivot, T(j,i) for lanes up to it
-//     a_ii -= L(i,j)^2    kept in a scalar: the NEXT pivot leaves through SHFL without waiting for the broadcast.
-// Results go to S: row (c0+i): columns c0..c0+i = L(i, :), columns c0+i+1..c0+32 = T(:, i) (T(r,i) at column c0+r+1),
-// the layout every consumer below reads (T(r, c) = S[c][r + 1]).
+// The 32-column slab of the diagonal block (columns c0..c0+31, all rows from c0 down to 127), matrixops.cpp:74-98 on it.
+// Measured (tools/chol32_microbench.cu, profiles/r2_chol32_microbench.txt): a whole 32x32 factorisation unrolled in one
+// warp is bound by instruction issue, not by its pivot chain (chain alone 120 clocks per column, with the 31-j column
+// updates 200-390 depending on how ptxas orders them).  So the pivot warp keeps only an 8-column panel in registers
+// (<= 7 updates per column), the rest of the slab follows on DMMA:
+//   pivot warp (rows c0..c0+31): per panel p -- 8 pivot columns (SHFL broadcasts, branch-free rsqrt), store, signal
+//                                barrier 1+p, then the rank-8 update of its own rows' remaining slab columns (DMMA)
+//   follower warps w = 1.. (rows c0+32w..): wait for barrier 1+p, solve their rows against the panel (8 columns),
+//                                store, rank-8 update of their rows (DMMA).  They never hold the pivot warp up.
+// 1/L(k,k) is left in rdg[] for the followers and for the inverse of the diagonal sub-block.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void chol32_inv(double* S, int c0, double* cb, int lane) {
-    double u[SBW];
+__device__ __forceinline__ double rsqrt_nb(double x) {
+    // MUFU.RSQ64H seed + the one cubic Newton step of CUDA's rsqrt(), without its special-case branch (which pins the
+    // whole column update between the Newton step and its use).  x <= 0 -> NaN / Inf, which propagates (matrixops.cpp:77).
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = y * y;
+    const double e = fma(-t, x, 1.0);
+    const double p2 = fma(e, 0.375, 0.5);
+    const double s = y * e;
+    return fma(p2, s, y);
+}
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// rank-8 update of rows [r0, r0 + 8 nrb) x slab columns [pc + 8, c0 + 32) by one warp:  S[R][C] -= sum_k S[R][pc+k] S[C][pc+k].
+// `tri`: the rows are the diagonal block's own (row block rb only needs column blocks up to its own).
+__device__ __forceinline__ void slab_rank8(double* S, int r0, int nrb, int c0, int p, bool tri, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    const int pc = c0 + 8 * p;
+    for (int cbk = p + 1; cbk < 4; cbk++) {
+        const int cc = c0 + 8 * cbk;
+        const double b0 = S[(cc + g) * LDS_ + pc + q], b1 = S[(cc + g) * LDS_ + pc + 4 + q];
+        for (int rb = 0; rb < nrb; rb++) {
+            const int rr = r0 + 8 * rb;
+            if (tri && rr < cc) continue;
+            double x0 = 0.0, x1 = 0.0;
+            dmma(x0, x1, S[(rr + g) * LDS_ + pc + q], b0);
+            dmma(x0, x1, S[(rr + g) * LDS_ + pc + 4 + q], b1);
+            double* dst = S + (rr + g) * LDS_ + cc + 2 * q;
+            dst[0] -= x0;
+            dst[1] -= x1;
+        }
+    }
+}
+
+// pivot warp: rows c0 + lane.  nfollow: follower warps to signal (0: none).
+__device__ __forceinline__ void slab_pivot(double* S, double* rdg, int c0, int nfollow, int lane) {
+    double* row = S + (c0 + lane) * LDS_ + c0;
+#pragma unroll 1
+    for (int p = 0; p < 4; p++) {
+        const int pl0 = 8 * p;
+        double a[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) a[c] = (lane >= pl0) ? row[pl0 + c] : 0.0;
+        double ajj = __shfl_sync(0xffffffffu, a[0], pl0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int pl = pl0 + j;                       // pivot lane
+            const double rd = rsqrt_nb(ajj);
+            const double d = ajj * rd;                    // sqrt(a_jj) without the sqrt -> divide chain
+            const double la = (lane > pl) ? a[j] * rd : (lane == pl ? d : 0.0);
+            a[j] = la;
+            if (lane == pl) rdg[c0 + pl] = rd;
+            if (j + 1 < 8) {
+                const double pvn = fma(-la, la, a[j + 1]);               // next pivot, valid in lane pl + 1
+                ajj = __shfl_sync(0xffffffffu, pvn, pl + 1);
+#pragma unroll
+                for (int c = j + 1; c < 8; c++) {
+                    const double lc = __shfl_sync(0xffffffffu, la, pl0 + c);   // L(pl0 + c, pl)
+                    a[c] = fma(-la, lc, a[c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+            if (lane >= pl0 + c) row[pl0 + c] = a[c];      // lower part only: the upper part of S holds the inverses
+        __syncwarp();
+        if (nfollow > 0) named_arrive(1 + p, 32 * (1 + nfollow));
+        if (p < 3) {
+            slab_rank8(S, c0 + 8 * (p + 1), 3 - p, c0, p, true, lane);
+            __syncwarp();
+        }
+    }
+}
+
+// follower warp w >= 1: rows c0 + 32 w + lane.
+__device__ __forceinline__ void slab_follow(double* S, const double* rdg, int c0, int w, int nfollow, int lane) {
+    double* row = S + (c0 + 32 * w + lane) * LDS_ + c0;
+#pragma unroll 1
+    for (int p = 0; p < 4; p++) {
+        const int pl0 = 8 * p;
+        double b[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) b[c] = row[pl0 + c];
+        named_bar(1 + p, 32 * (1 + nfollow));             // the pivot warp has stored panel p and its 1/L(k,k)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double lb = b[j] * rdg[c0 + pl0 + j];
+            b[j] = lb;
+#pragma unroll
+            for (int c = j + 1; c < 8; c++) b[c] = fma(-lb, S[(c0 + pl0 + c) * LDS_ + c0 + pl0 + j], b[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) row[pl0 + c] = b[c];
+        __syncwarp();
+        if (p < 3) {
+            slab_rank8(S, c0 + 32 * w, 4, c0, p, false, lane);
+            __syncwarp();
+        }
+    }
+}
+
+// inverse of the 32x32 diagonal sub-block at c0 by one warp: lane c solves L x = e_c (matrixops.cpp:330-340);
+// T(k, c) goes to S[c0 + c][c0 + k + 1] (the layout every consumer reads: T(r, c) = S[c][r + 1]).
+__device__ __forceinline__ void inv32_warp(double* S, const double* rdg, int c0, int lane) {
+    double r[SBW];
+#pragma unroll
+    for (int i = 0; i < SBW; i++) r[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < SBW; k++) {
+        const double x = r[k] * rdg[c0 + k];
+        r[k] = x;
+#pragma unroll
+        for (int i = k + 1; i < SBW; i++) r[i] = fma(-S[(c0 + i) * LDS_ + c0 + k], x, r[i]);
+    }
     double* row = S + (c0 + lane) * LDS_ + c0;
 #pragma unroll
-    for (int c = 0; c < SBW; c++) u[c] = (c < lane) ? row[c] : 0.0;
-    double adiag = row[lane];
-    double ldiag = 0.0, tdiag = 0.0;
-    double ajj = __shfl_sync(0xffffffffu, adiag, 0);
-#pragma unroll
-    for (int j = 0; j < SBW; j++) {
-        const double rd = rsqrt(ajj);          // negative pivot -> NaN, propagates (matrixops.cpp:77)
-        const double d = ajj * rd;             // sqrt(a_jj) without the sqrt -> divide chain
-        const double val = u[j] * rd;
-        const double l = (lane > j) ? val : 0.0;                    // L(lane, j)
-        const double m = (lane == j) ? rd : val;                    // multiplier of the column update
-        if (lane == j) {
-            ldiag = d;
-            tdiag = rd;
-        }
-        u[j] = val;
-        if (j + 1 < SBW) {
-            adiag = fma(-l, l, adiag);                               // a_ii -= L(i,j)^2
-            ajj = __shfl_sync(0xffffffffu, adiag, j + 1);            // next pivot: on its way before the broadcast
-            double* buf = cb + (j & 1) * SBW;
-            buf[lane] = (lane > j) ? val : 0.0;
-            __syncwarp();
-            if (lane == j) {
-#pragma unroll
-                for (int c = j + 1; c < SBW; c++) u[c] = 0.0;        // column `lane` of T starts from e_lane
-            }
-#pragma unroll
-            for (int c = j + 1; c < SBW; c++) u[c] = fma(-buf[c], m, u[c]);
-        }
-    }
-#pragma unroll
-    for (int p = 0; p <= SBW; p++) {
-        double v;
-        if (p < lane) v = u[p < SBW ? p : 0];
-        else if (p == lane) v = ldiag;
-        else if (p == lane + 1) v = tdiag;
-        else v = u[p > 0 ? p - 1 : 0];
-        row[p] = v;
-    }
+    for (int k = 0; k < SBW; k++)
+        if (k >= lane) row[k + 1] = r[k];
 }
 
 __device__ __forceinline__ long long gtime() {
@@ -179,11 +257,10 @@ struct StepArgs {
     double* A;
     int64_t ld, sA;
     int n, nrows, j0;
-    double* invd;          // [batch][nblk][128][128]
-    int64_t sInvd;
+    double* pub;           // [batch][128][132]: image of DIAG's shared tile (L11 lower, T_cc at [c][r + 1]), row block by row block
     double* logdet_part;   // [batch][nblk]
     int nblk, blk;
-    int* sync;             // [batch][nblk][4]: ticket, SYRKD counter, DIAG flag
+    int* sync;             // [batch][nblk][4]: ticket, SYRKD counter, DIAG row blocks published (0..4)
     int prologue;
     int nrow_tiles;
     long long* stamps;
@@ -191,6 +268,23 @@ struct StepArgs {
 
 // Shared memory: Lb [128][132] | As [32][132] | Cs [32][132] | cb [2][32] | red [128] | role
 constexpr size_t STEP_SMEM = (size_t)(DB * LDS_ + 2 * SBW * LDS_ + 2 * SBW + DB) * sizeof(double) + 16;
+
+// DIAG: rows [32 r, 32 r + 32) of the shared tile are final (L(r, 0..r) and T_rr): copy them to the published image
+// and the L part into the matrix.  Threads t = first, first + count, ...
+__device__ __forceinline__ void publish_rows(const double* S, double* pub, double* A, int64_t ld, int j0, int nb, int r,
+                                             int t, int count) {
+    constexpr int CH = LDS_ / 2;   // 16-byte chunks per row
+    for (int e = t; e < SBW * CH; e += count) {
+        const int i = SBW * r + e / CH, c = (e % CH) * 2;
+        const double2 v = *reinterpret_cast<const double2*>(S + i * LDS_ + c);
+        *reinterpret_cast<double2*>(pub + i * LDS_ + c) = v;
+        if (i < nb) {
+            double* dst = A + (int64_t)(j0 + i) * ld + j0 + c;
+            if (c + 1 <= i) *reinterpret_cast<double2*>(dst) = v;
+            else if (c == i) dst[0] = v.x;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(NT, 1) chol_step_kernel(const StepArgs p) {
     extern __shared__ __align__(16) double sm[];
@@ -204,6 +298,7 @@ __global__ void __launch_bounds__(NT, 1) chol_step_kernel(const StepArgs p) {
     const int g = lane >> 2, q = lane & 3;
     const int64_t b = blockIdx.y;
     double* A = p.A + b * p.sA;
+    double* pub = p.pub + b * (DB * LDS_);
     int* sync = p.sync + (b * p.nblk + p.blk) * 4;
     const int j0 = p.j0, n = p.n;
     const int nb = min(DB, n - j0);          // columns of this block (< 128 only for the last one)
@@ -224,10 +319,17 @@ __global__ void __launch_bounds__(NT, 1) chol_step_kernel(const StepArgs p) {
         if (ticket == 0) STEP_STAMP(0, 0);
         load_tile(As, A + (int64_t)ri * p.ld + pj, p.ld, SBW, n - ri, DB, tid, A);
         load_tile(Cs, A + (int64_t)rj * p.ld + pj, p.ld, SBW, n - rj, DB, tid, A);
+        {   // the 32x32 block itself (one 16-byte chunk per thread), so the update is not a dependent global round trip
+            const int r = tid >> 4, c = (tid & 15) * 2;
+            int bytes = (n - (rj + c)) * 8;
+            bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+            if (ri + r >= n) bytes = 0;
+            cp_async16(Lb + r * LDS_ + c, bytes ? A + (int64_t)(ri + r) * p.ld + rj + c : A, bytes);
+        }
         cp_async_wait_all();
         __syncthreads();
         if (ticket == 0) STEP_STAMP(0, 1);
-        // warp w: 8x8 block (w / 4, w % 4) of the 32x32 output, K = 128
+        // warp w: 8x8 block (w / 4, w % 4) of the 32x32 output, K = 128 on two accumulator chains
         const int r8 = (warp >> 2) * 8, c8 = (warp & 3) * 8;
         double acc[1][1][2] = {{{0.0, 0.0}}};
         double acc2[1][1][2] = {{{0.0, 0.0}}};
@@ -238,8 +340,9 @@ __global__ void __launch_bounds__(NT, 1) chol_step_kernel(const StepArgs p) {
         const int gi = ri + r8 + g, gj = rj + c8 + 2 * q;
         if (gi < n) {
             double* dst = A + (int64_t)gi * p.ld + gj;
-            if (gj <= gi && gj < n) dst[0] -= acc[0][0][0] + acc2[0][0][0];
-            if (gj + 1 <= gi && gj + 1 < n) dst[1] -= acc[0][0][1] + acc2[0][0][1];
+            const double* old = Lb + (r8 + g) * LDS_ + c8 + 2 * q;
+            if (gj <= gi && gj < n) dst[0] = old[0] - (acc[0][0][0] + acc2[0][0][0]);
+            if (gj + 1 <= gi && gj + 1 < n) dst[1] = old[1] - (acc[0][0][1] + acc2[0][0][1]);
         }
         __threadfence();
         __syncthreads();
@@ -254,7 +357,7 @@ __global__ void __launch_bounds__(NT, 1) chol_step_kernel(const StepArgs p) {
         STEP_STAMP(1, 0);
         if (nsy) {
             if (tid == 0)
-                while (ld_acquire(&sync[1]) < NSYRKD) __nanosleep(40);
+                while (ld_acquire(&sync[1]) < NSYRKD) __nanosleep(20);
             __syncthreads();
         }
         STEP_STAMP(1, 1);
@@ -265,116 +368,91 @@ __global__ void __launch_bounds__(NT, 1) chol_step_kernel(const StepArgs p) {
         if (tid < DB && tid >= nb) S[tid * LDS_ + tid] = 1.0;   // identity padding of the last block
         __syncthreads();
 
+        double* rdg = red;   // 1 / L(k,k); `red` is only needed for the log-determinant at the very end
+        constexpr int NH = NWARP - 4, HT = NH * 32;    // helper warps 4..15
         for (int c = 0; c < DB / SBW; c++) {
             const int c0 = c * SBW;
+            const int nfollow = DB / SBW - 1 - c;        // 32-row groups below the diagonal sub-block
             if (warp == 0) {
-                chol32_inv(S, c0, cb, lane);
-            } else if (c > 0) {
-                // remainder of panel c-1 (rows below the next diagonal sub-block), warps 1..15:
-                //   X = A[R, p0:p0+32] T_pp^T  for R = [c0 + 32, 128), then  A[R, c0:] -= X X[c0:, :]^T (lower part)
-                const int p0 = c0 - SBW, R0 = c0 + SBW, nr = DB - R0;
-                if (nr > 0) {
-                    const int w = warp - 1;
-                    // TRSM blocks: (nr/8) x 4, results to registers first (in place: every block reads the whole strip)
-                    double v0[3], v1[3];
-                    int rr[3], cc[3], cnt = 0;
+                if (p.stamps && blockIdx.y == 0 && c == 0) {
+                    const long long t = clock64();
+                    if (lane == 0) p.stamps[(p.blk * 3 + 1) * 16 + 13] = t;
+                }
+                slab_pivot(S, rdg, c0, nfollow, lane);
+                if (p.stamps && blockIdx.y == 0 && c == 0) {
+                    const long long t = clock64();
+                    if (lane == 0) p.stamps[(p.blk * 3 + 1) * 16 + 14] = t;
+                }
+            } else if (warp <= nfollow) {
+                slab_follow(S, rdg, c0, warp, nfollow, lane);
+            } else if (warp >= 4 && c > 0) {
+                // helpers, in the shadow of slab c: what slab c-1 left behind
+                const int p0 = c0 - SBW;                 // previous slab's columns
+                if (warp == 4) {
+                    inv32_warp(S, rdg, p0, lane);        // T_(c-1)
+                } else {
+                    // rest of SYRK(c-1): rows >= c0 + 32, columns c0 + 32 .. row (slab c only touches columns < c0 + 32)
+                    const int R0 = c0 + SBW, nrb = (DB - R0) / 8;
                     blocks_mma(
-                        w, NWARP - 1, (nr / 8) * 4,
-                        [&](int x, int& r0, int& cc0, int& klo, int& khi) {
-                            r0 = R0 + (x >> 2) * 8;
-                            cc0 = (x & 3) * 8;
-                            klo = 0;
-                            khi = cc0 + 8;   // T_pp lower triangular: k <= j
-                        },
-                        [&](int i, int k) { return S[i * LDS_ + p0 + k]; },
-                        [&](int k, int j) { return k <= j ? S[(p0 + k) * LDS_ + p0 + j + 1] : 0.0; },   // T(j, k)
-                        [&](int i, int j, double a, double bb) {
-                            if (cnt < 3) { rr[cnt] = i; cc[cnt] = j; v0[cnt] = a; v1[cnt] = bb; }
-                            cnt++;
-                        },
-                        lane);
-                    named_bar(1, NT - 32);
-                    for (int t = 0; t < cnt && t < 3; t++) {
-                        S[rr[t] * LDS_ + p0 + cc[t]] = v0[t];
-                        S[rr[t] * LDS_ + p0 + cc[t] + 1] = v1[t];
-                    }
-                    named_bar(1, NT - 32);
-                    // SYRK blocks: rows R (8-row blocks rb), columns c0 .. row block's diagonal: lower 8x8 blocks
-                    const int nrb = nr / 8, cb0 = SBW / 8;   // column blocks left of R0: cb0 (the c0..R0 strip), then rb + 1
-                    const int total = nrb * cb0 + nrb * (nrb + 1) / 2;
-                    blocks_mma(
-                        w, NWARP - 1, total,
+                        warp - 5, NH - 1, nrb * (nrb + 1) / 2,
                         [&](int x, int& r0, int& cc0, int& klo, int& khi) {
                             klo = 0;
                             khi = SBW;
-                            if (x < nrb * cb0) {
-                                r0 = R0 + (x / cb0) * 8;
-                                cc0 = c0 + (x % cb0) * 8;
-                            } else {
-                                int y = x - nrb * cb0, rb = 0;
-                                while (y > rb) {
-                                    y -= rb + 1;
-                                    rb++;
-                                }
-                                r0 = R0 + rb * 8;
-                                cc0 = R0 + y * 8;
+                            int y = x, rb = 0;
+                            while (y > rb) {
+                                y -= rb + 1;
+                                rb++;
                             }
+                            r0 = R0 + rb * 8;
+                            cc0 = R0 + y * 8;
                         },
                         [&](int i, int k) { return S[i * LDS_ + p0 + k]; },
                         [&](int k, int j) { return S[j * LDS_ + p0 + k]; },
                         [&](int i, int j, double a, double bb) {
-                            S[i * LDS_ + j] -= a;
-                            S[i * LDS_ + j + 1] -= bb;
+                            if (j <= i) S[i * LDS_ + j] -= a;
+                            if (j + 1 <= i) S[i * LDS_ + j + 1] -= bb;
                         },
                         lane);
                 }
+                named_bar(5, HT);
+                publish_rows(S, pub, A, p.ld, j0, nb, c - 1, tid - 128, HT);
+                __threadfence();
+                named_bar(6, HT);
+                if (tid == 128) st_release(&sync[2], c);
             }
             __syncthreads();
             STEP_STAMP(1, 3 + 2 * c);
             if (c0 + SBW >= DB) break;
-            // critical part of panel c: the next 32 rows.  X = A[c0+32 : c0+64, c0 : c0+32] T_cc^T, one 8x8 block per warp
+            // critical part of SYRK(c): columns c0+32 .. c0+63 of every row below (lower part), K = 32 -- what slab c+1 reads
             {
-                const int R0 = c0 + SBW;
-                const int r8 = R0 + (warp >> 2) * 8, c8 = (warp & 3) * 8;
-                double a0 = 0.0, a1 = 0.0;
-                for (int k = 0; k < c8 + 8; k += 4)   // T_cc(j, k) = S[c0 + k][c0 + j + 1] for k <= j
-                    dmma(a0, a1, S[(r8 + g) * LDS_ + c0 + k + q], k + q <= c8 + g ? S[(c0 + k + q) * LDS_ + c0 + c8 + g + 1] : 0.0);
-                __syncthreads();
-                S[(r8 + g) * LDS_ + c0 + c8 + 2 * q] = a0;
-                S[(r8 + g) * LDS_ + c0 + c8 + 2 * q + 1] = a1;
-                __syncthreads();
-                // next diagonal sub-block: A[R0:R0+32, R0:R0+32] -= X X^T, 10 lower 8x8 blocks
-                if (warp < 10) {
-                    int bi = 0, bj = warp;
-                    while (bj > bi) {
-                        bj -= bi + 1;
-                        bi++;
-                    }
-                    double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
-                    for (int k = 0; k < SBW; k += 8) {
-                        dmma(s0, s1, S[(R0 + bi * 8 + g) * LDS_ + c0 + k + q], S[(R0 + bj * 8 + g) * LDS_ + c0 + k + q]);
-                        dmma(t0, t1, S[(R0 + bi * 8 + g) * LDS_ + c0 + k + 4 + q], S[(R0 + bj * 8 + g) * LDS_ + c0 + k + 4 + q]);
-                    }
-                    S[(R0 + bi * 8 + g) * LDS_ + R0 + bj * 8 + 2 * q] -= s0 + t0;
-                    S[(R0 + bi * 8 + g) * LDS_ + R0 + bj * 8 + 2 * q + 1] -= s1 + t1;
-                }
+                const int R0 = c0 + SBW, nrb = (DB - R0) / 8;
+                blocks_mma(
+                    warp, NWARP, nrb * 4,
+                    [&](int x, int& r0, int& cc0, int& klo, int& khi) {
+                        r0 = R0 + (x >> 2) * 8;
+                        cc0 = R0 + (x & 3) * 8;
+                        klo = 0;
+                        khi = cc0 <= r0 ? SBW : 0;      // blocks above the diagonal: nothing to do
+                    },
+                    [&](int i, int k) { return S[i * LDS_ + c0 + k]; },
+                    [&](int k, int j) { return S[j * LDS_ + c0 + k]; },
+                    [&](int i, int j, double a, double bb) {
+                        if (j <= i) S[i * LDS_ + j] -= a;
+                        if (j + 1 <= i) S[i * LDS_ + j + 1] -= bb;
+                    },
+                    lane);
                 __syncthreads();
                 STEP_STAMP(1, 4 + 2 * c);
             }
         }
+        if (warp == 0) inv32_warp(S, rdg, DB - SBW, lane);
+        __syncthreads();
 
-        // write back: L11 (lower) into A, the four 32x32 diagonal inverses into invd; then release the flag
-        double* inv = p.invd + b * p.sInvd + (int64_t)p.blk * DB * DB;
-        for (int e = tid; e < DB * DB; e += NT) {
-            const int i = e >> 7, j = e & (DB - 1);
-            if (j <= i) {
-                if (i < nb) A[(int64_t)(j0 + i) * p.ld + j0 + j] = S[i * LDS_ + j];
-                if ((i >> 5) == (j >> 5)) inv[i * DB + j] = S[j * LDS_ + i + 1];
-            }
-        }
+        // last row block, then the flag every row tile's final sub-step waits for
+        publish_rows(S, pub, A, p.ld, j0, nb, DB / SBW - 1, tid, NT);
         __threadfence();
         __syncthreads();
-        if (tid == 0) st_release(&sync[2], 1);
+        if (tid == 0) st_release(&sync[2], DB / SBW);
         STEP_STAMP(1, 11);
         if (p.logdet_part) {
             if (tid < DB) red[tid] = log(S[tid * LDS_ + tid]);
@@ -426,28 +504,25 @@ __global__ void __launch_bounds__(NT, 1) chol_step_kernel(const StepArgs p) {
     }
     __syncthreads();   // Lb is free again, Cs holds the updated tile
     if (st0) STEP_STAMP(2, 2);
-    if (tid == 0)
-        while (ld_acquire(&sync[2]) == 0) __nanosleep(40);
-    __syncthreads();
-    if (st0) STEP_STAMP(2, 3);
-    load_tile(Lb, A + (int64_t)j0 * p.ld + j0, p.ld, DB, nb, nb, tid, A);
-    cp_async_wait_all();
-    __syncthreads();
-    {
-        // T_cc blocks into the transposed-upper positions: T(i, j) at Lb[j][i + 1] (same layout as DIAG's S)
-        const double* inv = p.invd + b * p.sInvd + (int64_t)p.blk * DB * DB;
-        for (int e = tid; e < 4 * SBW * SBW; e += NT) {
-            const int c = e >> 10, i = (e >> 5) & 31, j = e & 31;
-            if (j <= i) Lb[(c * SBW + j) * LDS_ + c * SBW + i + 1] = __ldcg(inv + (c * SBW + i) * DB + c * SBW + j);
-        }
-    }
-    __syncthreads();
-    if (st0) STEP_STAMP(2, 4);
-    // blocked substitution, one 8x8 block of the 32x32 step per warp
+    // blocked substitution, sub-step c as soon as DIAG has published row block c (L(c, 0..c) and T_cc); one 8x8 block of
+    // the 32x32 sub-step per warp.  Only the last sub-step is exposed after DIAG's last panel.
     const int r8 = (warp >> 2) * 8, c8 = (warp & 3) * 8;
     for (int c = 0; c < DB / SBW; c++) {
         const int c0 = c * SBW;
         if (c0 >= nb) break;
+        if (tid == 0)
+            while (ld_acquire(&sync[2]) <= c) __nanosleep(20);
+        __syncthreads();
+        if (st0) STEP_STAMP(2, 3 + c);
+        {
+            constexpr int CH = LDS_ / 2;
+            for (int e = tid; e < SBW * CH; e += NT) {
+                const int i = c0 + e / CH, cc = (e % CH) * 2;
+                cp_async16(Lb + i * LDS_ + cc, pub + i * LDS_ + cc, 16);
+            }
+            cp_async_wait_all();
+            __syncthreads();
+        }
         if (c > 0) {
             double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
             for (int k = 0; k < c0; k += 8) {
@@ -467,7 +542,7 @@ __global__ void __launch_bounds__(NT, 1) chol_step_kernel(const StepArgs p) {
         Cs[(r8 + g) * LDS_ + c0 + c8 + 2 * q + 1] = x1;
         __syncthreads();
     }
-    if (st0) STEP_STAMP(2, 5);
+    if (st0) STEP_STAMP(2, 7);
     // write X back (rows < nrows, columns < nb)
     for (int e = tid; e < SBW * (DB / 2); e += NT) {
         const int r = e >> 6, c = (e & 63) * 2;
@@ -477,7 +552,7 @@ __global__ void __launch_bounds__(NT, 1) chol_step_kernel(const StepArgs p) {
             else if (c < nb) dst[0] = Cs[r * LDS_ + c];
         }
     }
-    if (st0) STEP_STAMP(2, 6);
+    if (st0) STEP_STAMP(2, 8);
 }
 
 static long long* g_step_stamps = nullptr;
@@ -485,9 +560,10 @@ static long long* g_step_stamps = nullptr;
 }  // namespace
 
 void set_step_stamps(long long* dev) { g_step_stamps = dev; }
+size_t chol_step_pub_doubles(int batch) { return (size_t)batch * DB * LDS_; }
 
-void launch_chol_step(double* A, int64_t ld, int64_t sA, int n, int nrows, int j0, double* invd, int64_t sInvd,
-                      double* logdet_part, int nblk, int* sync, int prologue, int batch, cudaStream_t st) {
+void launch_chol_step(double* A, int64_t ld, int64_t sA, int n, int nrows, int j0, double* pub, double* logdet_part, int nblk,
+                      int* sync, int prologue, int batch, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         CUGP_CUDA(cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM));
@@ -495,7 +571,7 @@ void launch_chol_step(double* A, int64_t ld, int64_t sA, int n, int nrows, int j
     }
     StepArgs p{};
     p.A = A; p.ld = ld; p.sA = sA; p.n = n; p.nrows = nrows; p.j0 = j0;
-    p.invd = invd; p.sInvd = sInvd; p.logdet_part = logdet_part; p.nblk = nblk; p.blk = j0 / DB;
+    p.pub = pub; p.logdet_part = logdet_part; p.nblk = nblk; p.blk = j0 / DB;
     p.sync = sync; p.prologue = prologue; p.stamps = g_step_stamps;
     const int nb = std::min(DB, n - j0);
     const int below = nrows - (j0 + nb);

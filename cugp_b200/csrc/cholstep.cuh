@@ -6,11 +6,13 @@ namespace cugp {
 
 // One launch = SYRK prologue of the diagonal block (if `prologue`) + 128x128 POTRF with its four 32x32 diagonal
 // inverses + (prologue and) TRSM of every 32-row tile below, rows [.., nrows) (nrows > n: appended right-hand sides).
-// `sync`: int[batch][nblk][4], zeroed before the first step of a factorisation.  With `prologue` the block column
-// j0 - 128 must be final and must NOT have been applied to block column j0 yet (the launch applies it).
-// The off-diagonal 32x32 blocks of invd are NOT written: launch_trtri_diag_all() completes them afterwards.
-void launch_chol_step(double* A, int64_t ld, int64_t sA, int n, int nrows, int j0, double* invd, int64_t sInvd,
-                      double* logdet_part, int nblk, int* sync, int prologue, int batch, cudaStream_t st);
+// `sync`: int[batch][nblk][4], zeroed before the first step of a factorisation.  `pub`: chol_step_pub_doubles(batch)
+// doubles of scratch (the diagonal CTA publishes its tile there, row block by row block, for the row tiles).  With
+// `prologue` the block column j0 - 128 must be final and must NOT have been applied to block column j0 yet (the launch
+// applies it).  The 128x128 inverses of the diagonal blocks are NOT produced: launch_trtri_diag() afterwards.
+void launch_chol_step(double* A, int64_t ld, int64_t sA, int n, int nrows, int j0, double* pub, double* logdet_part, int nblk,
+                      int* sync, int prologue, int batch, cudaStream_t st);
+size_t chol_step_pub_doubles(int batch);
 
 // Tuning aid: device buffer [nblk][3][16] of globaltimer stamps written by every step (nullptr: off).
 void set_step_stamps(long long* dev);

@@ -58,6 +58,8 @@ void set_overlap_inverse(int max_n, int cap) {
     if (cap > 0) g_overlap_cap = cap;
     bump_tuning_epoch();
 }
+static int g_pred_chunk = 0;  // > 0: at most this many test points per prediction chunk (tests: several chunks at small m)
+void set_pred_chunk(int v) { g_pred_chunk = v; }
 static int g_lookahead = 1;
 void set_lookahead(int v) { g_lookahead = v; bump_tuning_epoch(); }
 bool lookahead_enabled() { return g_lookahead != 0; }
@@ -152,13 +154,13 @@ static void potrf_trailing(double* A, int64_t ld, int64_t sA, int nrows, int J0,
 // Both step(J+2) and U2(J) touch block column J+2: step(J+2) waits for U2(J).
 static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, double* invd, int64_t sInvd, double* logdet_part,
                         int nblk, int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la,
-                        int* stepsync) {
+                        int* stepsync, double* steppub) {
     CUGP_CUDA(cudaMemsetAsync(stepsync, 0, (size_t)batch * nblk * 4 * sizeof(int), st));
     const bool ahead = la && la->st2 && nblk >= 3 && lookahead_enabled();
     if (!ahead) {
         for (int J = 0; J < nblk; J++) {
             const int J0 = J * kDiag, Jend = std::min(n, J0 + kDiag), Jend2 = std::min(n, Jend + kDiag);
-            launch_chol_step(A, ld, sA, n, nrows, J0, invd, sInvd, logdet_part, nblk, stepsync, J > 0, batch, st);
+            launch_chol_step(A, ld, sA, n, nrows, J0, steppub, logdet_part, nblk, stepsync, J > 0, batch, st);
             if (launches) ++*launches;
             potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend2, n, batch, st, launches, prof);
         }
@@ -180,7 +182,7 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
     for (int J = 0; J < nblk; J++) {
         const int J0 = J * kDiag, Jend = std::min(n, J0 + kDiag), Jend2 = std::min(n, Jend + kDiag);
         if (J >= 2) CUGP_CUDA(cudaStreamWaitEvent(s2, evU(J - 2), 0));
-        launch_chol_step(A, ld, sA, n, nrows, J0, invd, sInvd, logdet_part, nblk, stepsync, J > 0, batch, s2);
+        launch_chol_step(A, ld, sA, n, nrows, J0, steppub, logdet_part, nblk, stepsync, J > 0, batch, s2);
         if (launches) ++*launches;
         if (Jend2 >= n) continue;   // nothing right of block J+1
         CUGP_CUDA(cudaEventRecord(evP(J), s2));
@@ -195,15 +197,16 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
 }
 
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part, int batch,
-                   cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la, int rhs_rows, int* stepsync) {
+                   cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la, int rhs_rows, int* stepsync,
+                   double* steppub) {
     if (prof && !prof->on) prof = nullptr;
     const int nrows = n + rhs_rows;
     const int nblk = cdiv(n, kDiag);
     const int NB = potrf_outer_width(n);
     const int npanels = cdiv(n, NB);
     if (la) la->panel_events = false;
-    if (stepsync && g_fused_step && NB == kDiag) {
-        potrf_fused(A, ld, sA, n, nrows, invd, sInvd, logdet_part, nblk, batch, st, launches, prof, la, stepsync);
+    if (stepsync && steppub && g_fused_step && NB == kDiag) {
+        potrf_fused(A, ld, sA, n, nrows, invd, sInvd, logdet_part, nblk, batch, st, launches, prof, la, stepsync, steppub);
         return;
     }
     if (!la || !la->st2 || npanels < 3 || !lookahead_enabled()) {
@@ -333,13 +336,14 @@ GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(
     dalloc(tpart, trsv_backward_scratch(n, B));
     dalloc(gradout, (size_t)B * 3);
     dalloc(stepsync, (size_t)B * nblk * 4);
+    dalloc(steppub, chol_step_pub_doubles(B));
 }
 
 GpBatch::~GpBatch() {
     if (st) cudaStreamSynchronize(st);
     dfree(X); dfree(y); dfree(Kb); dfree(invd); dfree(logdet_part); dfree(work); dfree(alpha); dfree(scal);
-    dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout); dfree(tpart); dfree(stepsync);
-    dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar);
+    dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout); dfree(tpart); dfree(stepsync); dfree(steppub);
+    dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar); dfree(Xt_all);
     if (hstage) cudaFreeHost(hstage);
     if (hres) cudaFreeHost(hres);
     for (cudaEvent_t e : prof.ev) cudaEventDestroy(e);
@@ -408,6 +412,11 @@ void GpBatch::adopt_device_data(const double* Xd, const double* yd, int b, cudaE
     CUGP_CUDA(cudaMemcpyAsync(y, yd, rows * sizeof(double), cudaMemcpyDeviceToDevice, st));
     have_data = true;
     invalidate();
+}
+
+void GpBatch::eval_enqueue(bool want_grad) {
+    factorize();
+    if (want_grad) gradient_launch();
 }
 
 void GpBatch::eval_launch(bool want_grad) {
@@ -490,7 +499,7 @@ void GpBatch::build_K(int full) {
 void GpBatch::potrf(bool with_rhs) {
     auto body = [&] {
         potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la,
-                      with_rhs ? 1 : 0, stepsync);
+                      with_rhs ? 1 : 0, stepsync, steppub);
     };
     if (with_rhs || !run_graphed(graph_potrf, body)) body();   // graph_potrf holds the rhs-free sequence only
 }
@@ -501,7 +510,7 @@ void GpBatch::potrf_with_rhs() {
     auto body = [&] {
         launch_copy_rows(y, n, Kb + (int64_t)n * ld, mat_stride(), n, B, st);
         potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la, 1,
-                      stepsync);
+                      stepsync, steppub);
         const double* zrow = Kb + (int64_t)n * ld;
         launch_ll_finalize(zrow, zrow, mat_stride(), n, logdet_part, nblk, scal, B, st);
         launches += 2;
@@ -722,30 +731,21 @@ void GpBatch::ensure_pred(int mc) {
 
 // Predictive moments of every GP in the batch at m test points (covkernel.cpp:277-306):
 //   mean = k*' alpha ;  var = sf2 + sn2 - |L^-1 k*|^2  ( = sf2 + sn2 - k*' K^-1 k* ).
-// mean_h/var_h: [B][m] host (may be null).  PQ_dev: [2][m] device product-of-experts moments (may be null).
-void GpBatch::predict(const double* Xt_h, int m, double* mean_h, double* var_h, double* PQ_dev, int accumulate) {
+// Xt_dev: [m][dp] device, zero padded.  mean_h/var_h: [B][m] host (may be null).  PQ_dev: [2][m] device
+// product-of-experts moments (may be null).  Nothing here waits for the device unless host outputs were asked for.
+void GpBatch::predict_dev(const double* Xt_dev, int m, double* mean_h, double* var_h, double* PQ_dev, int accumulate) {
     if (m <= 0) return;
     trtri();
     solve();
     // chunk the test set so Kstar stays near 2 GB
     int64_t cap = (int64_t)(2.0e9 / ((double)Bcap * ld * 8.0));
     int mc = (int)std::min<int64_t>(m, std::max<int64_t>(64, cap / 64 * 64));
+    if (g_pred_chunk > 0) mc = std::min(mc, (int)round_up(g_pred_chunk, 64));
     ensure_pred(mc);
     const int tiles_j = cdiv(n, kCovTile);
     for (int t0 = 0; t0 < m; t0 += mc) {
         const int cur = std::min(mc, m - t0);
-        sync();
-        double* s = static_cast<double*>(stage((size_t)cur * dp * sizeof(double)));
-        if (dp == d) {
-            std::memcpy(s, Xt_h + (size_t)t0 * d, (size_t)cur * d * sizeof(double));
-        } else {
-            for (int r = 0; r < cur; r++) {
-                std::memcpy(s + (size_t)r * dp, Xt_h + (size_t)(t0 + r) * d, d * sizeof(double));
-                for (int k = d; k < dp; k++) s[(size_t)r * dp + k] = 0.0;
-            }
-        }
-        CUGP_CUDA(cudaMemcpyAsync(Xt, s, (size_t)cur * dp * sizeof(double), cudaMemcpyHostToDevice, st));
-        launch_cov_cross(Xt, cur, X, (int64_t)n * dp, n, dp, h, alpha, n, Ks, ld, (int64_t)mc * ld, meanpart,
+        launch_cov_cross(Xt_dev + (size_t)t0 * dp, cur, X, (int64_t)n * dp, n, dp, h, alpha, n, Ks, ld, (int64_t)mc * ld, meanpart,
                          (int64_t)tiles_j * mc, B, st);
         GemmParams p{};  // V = T Kstar^T ; only the column sums of squares are kept
         p.A = Tb; p.lda = ld; p.sA = mat_stride();
@@ -776,7 +776,31 @@ void GpBatch::predict(const double* Xt_h, int m, double* mean_h, double* var_h, 
             }
         }
     }
-    sync();
+    if (mean_h && var_h) sync();
+}
+
+// Host test points: packed to [m][dp] and uploaded ONCE (not per chunk), then predict_dev.
+void GpBatch::predict(const double* Xt_h, int m, double* mean_h, double* var_h, double* PQ_dev, int accumulate) {
+    if (m <= 0) return;
+    if (m > xt_all_cap) {
+        sync();
+        dfree(Xt_all);
+        dalloc(Xt_all, (size_t)m * dp);
+        xt_all_cap = m;
+    }
+    sync();   // the staging buffer may still feed an earlier copy
+    double* s = static_cast<double*>(stage((size_t)m * dp * sizeof(double)));
+    if (dp == d) {
+        std::memcpy(s, Xt_h, (size_t)m * d * sizeof(double));
+    } else {
+        for (int r = 0; r < m; r++) {
+            std::memcpy(s + (size_t)r * dp, Xt_h + (size_t)r * d, d * sizeof(double));
+            for (int k = d; k < dp; k++) s[(size_t)r * dp + k] = 0.0;
+        }
+    }
+    CUGP_CUDA(cudaMemcpyAsync(Xt_all, s, (size_t)m * dp * sizeof(double), cudaMemcpyHostToDevice, st));
+    predict_dev(Xt_all, m, mean_h, var_h, PQ_dev, accumulate);
+    if (!(mean_h && var_h)) sync();   // callers of the host-pointer variant expect the staging buffer to be free again
 }
 
 }  // namespace cugp

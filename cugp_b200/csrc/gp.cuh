@@ -37,9 +37,12 @@ struct GpBatch {
     double *gradpart = nullptr, *gradout = nullptr;
     double* tpart = nullptr;                // [B][8][n] partial sums of the backward sweep's panel launches
     int* stepsync = nullptr;                // [B][nblk][4] tickets / flags of the fused Cholesky block steps (cholstep.cu)
+    double* steppub = nullptr;              // [B][128][132] tile the diagonal CTA of a step publishes for its row tiles
     // prediction workspace (lazily sized)
     double *Xt = nullptr, *Ks = nullptr, *meanpart = nullptr, *css = nullptr, *pmean = nullptr, *pvar = nullptr;
     int pred_cap = 0;
+    double* Xt_all = nullptr;               // [xt_all_cap][dp] whole test set of the host-pointer predict()
+    int xt_all_cap = 0;
     // pinned host staging
     double* hstage = nullptr;
     size_t hstage_bytes = 0;
@@ -95,6 +98,7 @@ struct GpBatch {
     void set_active(int b);                 // 1 <= b <= Bcap; invalidates
     // One (LL [, gradient]) evaluation without a host wait: everything is queued on the stream and the results land in
     // the pinned staging buffer; eval_collect() waits and hands out [B] log-likelihoods and [B][3] gradients.
+    void eval_enqueue(bool want_grad);      // queue the evaluation only: scal / gradout stay on the device
     void eval_launch(bool want_grad);
     void eval_collect(double* ll_out, double* g_out);
     void set_theta(const double th[3]);
@@ -117,6 +121,8 @@ struct GpBatch {
     void gradient_launch();                 // queue trtri, alpha, lauum and the fused trace (gradout on the device)
     void gradient(double* g_out);           // [B][3] host, d(-LL)/dtheta
     void predict(const double* Xt_h, int m, double* mean_h, double* var_h, double* PQ_dev, int accumulate);
+    // test points already on the device ([m][dp], zero padded): no host wait unless mean_h / var_h are given
+    void predict_dev(const double* Xt_dev, int m, double* mean_h, double* var_h, double* PQ_dev, int accumulate);
     void get_alpha(double* out);            // [B][n] host
 
     void sync() { CUGP_CUDA(cudaStreamSynchronize(st)); }
@@ -130,7 +136,8 @@ struct GpBatch {
 // 128x128 diagonal blocks and per-block log-determinant partials as by-products.
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part,
                    int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr, PotrfLookahead* la = nullptr,
-                   int rhs_rows = 0, int* stepsync = nullptr);
+                   int rhs_rows = 0, int* stepsync = nullptr, double* steppub = nullptr);
+void set_pred_chunk(int v); // > 0: cap on the test points one prediction chunk carries (0: by memory)
 void set_fused_step(int v); // 1 (default): one fused launch per 128-column block step when the outer width is 128
 // Tuning epoch: bumped by every tuning change so cached graphs are re-captured.  graph_max_n: largest n whose launch
 // chains are replayed as CUDA graphs (0 disables).

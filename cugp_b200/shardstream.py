@@ -111,6 +111,11 @@ class ShardStream(BCM):
     def from_memory(cls, X, y, numchunks: int, rank=None, world=None, group=None, slots: int = 0):
         """Shards are consecutive blocks of ``len(y) // numchunks`` rows of (X, y), which stay on the host."""
         X, y = f64(X), f64(y)
+        if numchunks <= 0 or X.shape[0] % numchunks:
+            # the stream's shards all have numtrain rows (cuda_scalingdist/main.cpp:94-125); BCM's "last expert takes
+            # the remainder" (BCM.cpp:92-108) is the resident cugp_b200.BCM, not the stream
+            raise ValueError(f"ShardStream.from_memory: {X.shape[0]} rows do not split into {numchunks} equal shards; "
+                             "trim the data or use cugp_b200.BCM (its last expert takes the remainder)")
         numtrain = X.shape[0] // numchunks
         rank, world = cls._rank_world(rank, world, group)
         h = C.c_void_p()

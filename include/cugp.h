@@ -162,8 +162,27 @@ int cugp_bcm_predict_moments_dev(cugp_bcm *h, const double *Xtest, int m, double
 int cugp_bcm_predict_moments(cugp_bcm *h, const double *Xtest, int m, double *PQ);
 int cugp_poe_finalize_dev(const double *PQ_dev, int m, double *mean, double *var);
 int cugp_poe_finalize(const double *PQ, int m, double *mean, double *var);
-/* world == 1 convenience: the whole of BCM::compute_BCM_test_means_and_var */
+/* The whole of BCM::compute_BCM_test_means_and_var (BCM.cpp:64-83) over ALL experts: local moments, one
+ * ncclAllReduce(sum, f64, 2m) and the finalisation on the library's stream, one device->host copy.  world > 1 needs
+ * cugp_bcm_comm_init first; collective: every rank calls it with the same test points. */
 int cugp_bcm_predict(cugp_bcm *h, const double *Xtest, int m, double *mean, double *var);
+
+/* ---- the exchange step inside the library ---------------------------------------------
+ * Replaces the blocking-socket exchange of cuda_src/cg_solver.cpp:22-79 (workers write their LL / gradient to the
+ * master, the master adds and answers).  One process per GPU; NCCL is bound at run time (dlopen of libnccl.so.2). */
+#define CUGP_NCCL_ID_BYTES 128
+/* rank 0: a fresh NCCL unique id, to be handed to every rank by the caller's own means (MPI, a file, a store) */
+int cugp_nccl_unique_id(unsigned char id[CUGP_NCCL_ID_BYTES]);
+/* collective over the `world` ranks given to cugp_bcm_create: builds the communicator on the handle's device */
+int cugp_bcm_comm_init(cugp_bcm *h, const unsigned char id[CUGP_NCCL_ID_BYTES]);
+/* same, with a file as the rendezvous (rank 0 writes the id, the others wait up to timeout_s for it); `path` must be
+ * fresh for every communicator.  What include/cugp_shim/BCM.h uses under CUGP_RANK / CUGP_WORLD / CUGP_NCCL_ID_FILE. */
+int cugp_bcm_comm_init_file(cugp_bcm *h, const char *path, int timeout_s);
+int cugp_bcm_has_comm(cugp_bcm *h);        /* 1 once a communicator exists */
+long cugp_bcm_collectives(cugp_bcm *h);    /* NCCL collectives issued so far (one per operation) */
+/* BCM::get_BCM_loglikelihood + get_BCM_gradient_hyper (BCM.cpp:153-198) over ALL experts: local sums, then ONE
+ * ncclAllReduce(sum, f64, 4) behind them on the same stream; out4 = (LL, g0, g1, g2), identical on every rank. */
+int cugp_bcm_loglik_grad(cugp_bcm *h, int want_grad, double out4[4]);
 
 /* ---- shard streaming (cuda_scalingdist/cg_solver.cpp:42-70, main.cpp:94-125) -------------------------- */
 /* An expert ensemble whose shards do NOT stay on the GPU: shard i of `numchunks` holds `numtrain` rows of `dim`

@@ -117,6 +117,6 @@ class Covsum {
         cugp_nlpp(actual, predmean, predvar, TS, &out);
         return out;
     }
-    int get_param_dim() { return 3; }
+    int get_param_dim() { return numdim; }  // covkernel.cpp:661-663 returns numdim
 };
 #endif

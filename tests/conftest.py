@@ -67,7 +67,7 @@ def golden():
 
 
 # Tolerance policy (BASELINE.json north_star):
-#   log-likelihood, gradient: 1e-9 relative; a gradient component is gated against max(|g_k|, ||g||_inf)
+#   log-likelihood, gradient: 1e-9 relative; every gradient component against max(|g_k|, 1e-3 * ||g||_inf)
 #   predictive mean / variance: 1e-8 relative; means that are numerically zero in the reference
 #   (K ~ diagonal at theta_A) are gated against max(|ref|, 1e-12 * ||y||_inf ... ) i.e. absolutely.
 LL_RTOL = 1e-9
@@ -79,9 +79,16 @@ def assert_ll(got, ref, rtol=LL_RTOL):
     assert abs(got - ref) <= rtol * abs(ref), (got, ref, abs(got - ref) / abs(ref))
 
 
-def assert_grad(got, ref, rtol=LL_RTOL):
+GRAD_FLOOR = 1e-3   # a component is gated against max(|g_k|, GRAD_FLOOR * ||g||_inf)
+
+
+def assert_grad(got, ref, rtol=LL_RTOL, floor=GRAD_FLOOR):
+    """Every component on its own: |got_k - ref_k| <= rtol * max(|ref_k|, floor * ||ref||_inf).  The floor only
+    protects components that are cancellation noise next to the others (g0 ~ 1e-10 against g1 ~ 1e3 at theta_A, where
+    K is numerically diagonal: SURVEY.md section 8c); floor = 1 is the inf-norm gate SURVEY allows as the minimum."""
     got, ref = np.asarray(got, float), np.asarray(ref, float)
-    scale = np.maximum(np.abs(ref), np.max(np.abs(ref)))
+    scale = np.maximum(np.abs(ref), floor * np.max(np.abs(ref)))
+    assert np.all(np.isfinite(got)), got
     assert np.all(np.abs(got - ref) <= rtol * scale), (got, ref, np.abs(got - ref) / scale)
 
 

@@ -366,6 +366,51 @@ def test_bcm_rank_partials_sum_to_whole():
     whole.close()
 
 
+@pytest.mark.parametrize("chunk", [0, 256])
+def test_c4_prediction_at_600_points(chunk):
+    """C4 at m = 600 test points (golden from the unmodified reference, tests/golden/make_golden.py --group c4pred):
+    several row tiles of the variance GEMM's column-sum epilogue and -- with the chunk cap -- three test-set chunks."""
+    c, c1 = GOLD["C4_si24000_bcm16_thC_pred600"], GOLD["C4_expert0_n1500_thB_pred600"]
+    d = load_data("si24000")
+    Xt = np.ascontiguousarray(load_data("c4_xtest600")["Xtest"])
+    try:
+        assert lib().cugp_set_tuning(b"pred_chunk", chunk) == 0
+        b = cg.BCM(d["X"], d["y"], K=16, rank=0, world=1)
+        b.set_BCM_log_hyperparam(c["theta"])
+        mu, var = b.compute_BCM_test_means_and_var(Xt)
+        b.close()
+        assert_pred(mu, var, c["mean"], c["var"], yscale=np.abs(d["y"]).max())
+        g = cg.Covsum(1500, 10)
+        g.set_loghyperparam(c1["theta"])
+        mu, var = g.compute_test_means_and_variances(d["X"][:1500], d["y"][:1500], Xt)
+        g.close()
+        assert_pred(mu, var, c1["mean"], c1["var"], yscale=np.abs(d["y"]).max())
+    finally:
+        lib().cugp_set_tuning(b"pred_chunk", 0)
+
+
+@pytest.mark.parametrize("name", [n for n, c in GOLD.items() if c["kind"] == "kinv"])
+def test_k_inverse_and_cholesky_golden(name):
+    """compute_K_inverse / get_cholesky (matrixops.cpp:383-435, 68-108) at n = 1000 and 2048 against the unmodified
+    reference: every 37th row and column, the whole diagonal and the Frobenius norm."""
+    c = GOLD[name]
+    n, st = c["n"], c["stride"]
+    X = load_data("sine4096")["X"][:n]
+    K = PORT.K_train(X, c["theta"])
+    idx = np.arange(0, n, st)
+    Ki = cg.compute_K_inverse(K)
+    ref = np.array(c["Kinv_sample"]).reshape(len(idx), len(idx))
+    assert np.linalg.norm(Ki[np.ix_(idx, idx)] - ref) <= 1e-10 * np.linalg.norm(ref)
+    dref = np.array(c["Kinv_diag"])
+    assert np.linalg.norm(np.diag(Ki) - dref) <= 1e-10 * np.linalg.norm(dref)
+    assert abs(np.linalg.norm(Ki) - c["Kinv_fro"]) <= 1e-10 * c["Kinv_fro"]
+    assert np.array_equal(Ki, Ki.T)
+    L = cg.get_cholesky(K)
+    lref = np.array(c["L_sample"]).reshape(len(idx), len(idx))
+    assert np.linalg.norm(L[np.ix_(idx, idx)] - lref) <= 1e-12 * np.linalg.norm(lref)
+    assert abs(np.linalg.norm(L) - c["L_fro"]) <= 1e-12 * c["L_fro"]
+
+
 # ---------------------------------------------------------------------------------------------- API behaviour
 def test_loglik_then_grad_share_one_factorisation():
     c = GOLD["sine300_thB_pred7"]

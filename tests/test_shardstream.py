@@ -29,6 +29,14 @@ def _write_shards(tmp_path, X, y, chunks):
     return str(tmp_path / "in_"), str(tmp_path / "lab_"), n
 
 
+def test_from_memory_rejects_a_remainder():
+    """Shards of the stream are equally sized (cuda_scalingdist/main.cpp:94-125): rows that do not split evenly are an
+    error, not a silent truncation."""
+    import cugp_b200 as cg
+    with pytest.raises(ValueError):
+        cg.ShardStream.from_memory(np.zeros((10, 2)), np.zeros(10), 3)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("slots", [1, 2, 3, 0])
 def test_stream_from_memory_matches_oracle_bcm(slots):

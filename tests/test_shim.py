@@ -122,6 +122,7 @@ def test_shim_probe_runs_and_matches_python_mirror():
     assert np.array_equal(val["GRAD"], g.compute_gradient_loghyperparam(X[:n], y[:n]))
     mu, var = g.compute_test_means_and_variances(X[:n], y[:n], X[n:])
     assert val["PRED"] == [mu[0], var[0]]
+    assert val["NLPP"][1] == d == g.get_param_dim()   # Covsum::get_param_dim returns numdim (covkernel.cpp:661-663)
     assert val["CHOLDET"][2] < 1e-9          # forward + backward matrix substitution reproduce compute_K_inverse
     assert val["HOST"][0] < 1e-20            # K^-1 y (host helper on the GPU inverse) equals alpha
     b = cg.BCM(X[:n], y[:n], K=3, rank=0, world=1)

@@ -32,11 +32,12 @@ for n in [int(a) for a in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["15
             d, r, y_ = s[b, 1], s[b, 2], s[b, 0]
             nxt = (s[b + 1, 1, 0] - d[0]) / 1e3 if b + 1 < nblk else float("nan")
             dd = [(d[i] - d[0]) / 1e3 if d[i] else -1 for i in range(13)]
-            rr = [(r[i] - d[0]) / 1e3 if r[i] else -1 for i in range(7)]
+            rr = [(r[i] - d[0]) / 1e3 if r[i] else -1 for i in range(9)]
             yy = [(y_[i] - d[0]) / 1e3 if y_[i] else -1 for i in range(3)]
-            print(f"blk {b:2d} +{(d[0]-t0)/1e3:8.1f}us step {nxt:6.1f} | DIAG wait {dd[1]:5.1f} load {dd[2]:5.1f} p0 {dd[3]:5.1f}/{dd[4]:5.1f} p1 {dd[5]:5.1f}/{dd[6]:5.1f} "
+            cyc = d[14] - d[13]
+            print(f"blk {b:2d} chol32 {cyc} cyc +{(d[0]-t0)/1e3:8.1f}us step {nxt:6.1f} | DIAG wait {dd[1]:5.1f} load {dd[2]:5.1f} p0 {dd[3]:5.1f}/{dd[4]:5.1f} p1 {dd[5]:5.1f}/{dd[6]:5.1f} "
                   f"p2 {dd[7]:5.1f}/{dd[8]:5.1f} p3 {dd[9]:5.1f} flag {dd[11]:5.1f} end {dd[12]:5.1f} | ROWS0 start {rr[0]:5.1f} ld {rr[1]:5.1f} pro {rr[2]:5.1f} "
-                  f"flag {rr[3]:5.1f} L11 {rr[4]:5.1f} trsm {rr[5]:5.1f} end {rr[6]:5.1f} | SYRKD {yy[0]:5.1f} {yy[1]:5.1f} {yy[2]:5.1f}")
+                  f"flags {rr[3]:5.1f} {rr[4]:5.1f} {rr[5]:5.1f} {rr[6]:5.1f} trsm {rr[7]:5.1f} end {rr[8]:5.1f} | SYRKD {yy[0]:5.1f} {yy[1]:5.1f} {yy[2]:5.1f}")
             if b >= 13 and b < nblk - 3:
                 continue
         g.close()
