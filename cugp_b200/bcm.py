@@ -238,7 +238,7 @@ class BCM:
         m = Xt.shape[0]
         if m == 0:
             return np.empty(0), np.empty(0)
-        if self._in_library or (self.world == 1 and hasattr(self._local, "predict_all")):
+        if self._in_library or (self.world == 1 and isinstance(self._local, _CudaLocal)):
             return self._local.predict_all(Xt)
         nccl = self.world > 1 and self._dist is not None and self._dist.get_backend(self.group) == "nccl"
         if nccl and hasattr(self._local, "moments_into"):

@@ -149,6 +149,11 @@ int cugp_set_tuning(const char* key, long value) {
         set_pred_chunk((int)value);
         return CUGP_OK;
     }
+    if (std::strcmp(key, "fused_max_batch") == 0) {
+        if (value < 0) return CUGP_ERR_INVALID;
+        set_fused_max_batch((int)value);
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "fused_step") == 0) {
         set_fused_step(value != 0);
         return CUGP_OK;

@@ -11,7 +11,10 @@ namespace cugp {
 // `prologue` the block column j0 - 128 must be final and must NOT have been applied to block column j0 yet (the launch
 // applies it).  The 128x128 inverses of the diagonal blocks are NOT produced: launch_trtri_diag() afterwards.
 void launch_chol_step(double* A, int64_t ld, int64_t sA, int n, int nrows, int j0, double* pub, double* logdet_part, int nblk,
-                      int* sync, int prologue, int batch, cudaStream_t st);
+                      int* sync, int prologue, int batch, cudaStream_t st, int roles = 0);
+// roles = 0: one launch (the row tiles wait for the diagonal CTA on their SMs: only when every CTA of the launch is
+// resident at once); roles = 1 then roles = 2: diagonal part, then the row tiles, as two launches (wide batches).
+int chol_step_ctas(int n, int nrows, int j0);   // CTAs per matrix of a roles = 0 launch
 size_t chol_step_pub_doubles(int batch);
 
 // Tuning aid: device buffer [nblk][3][16] of globaltimer stamps written by every step (nullptr: off).

@@ -65,8 +65,9 @@ void set_lookahead(int v) { g_lookahead = v; bump_tuning_epoch(); }
 bool lookahead_enabled() { return g_lookahead != 0; }
 // Fused block step (cholstep.cu): one launch per 128 columns instead of diag kernel + TRSM GEMM + next-block update GEMM.
 // Used whenever the outer width is 128 (the latency-bound regime).  0 restores round 1's launch chain (A/B runs, tests).
-static int g_fused_step = 1;
+static int g_fused_step = 1, g_fused_max_batch = 10;
 void set_fused_step(int v) { g_fused_step = v; bump_tuning_epoch(); }
+void set_fused_max_batch(int v) { g_fused_max_batch = v; bump_tuning_epoch(); }
 static int g_potrf_nb = 0;  // 0: by size; otherwise forced (cugp_set_tuning("potrf_nb", v) or CUGP_POTRF_NB)
 void set_potrf_outer_width(int nb) { g_potrf_nb = nb; bump_tuning_epoch(); }
 int potrf_outer_width(int n) {
@@ -157,11 +158,28 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
                         int* stepsync, double* steppub) {
     CUGP_CUDA(cudaMemsetAsync(stepsync, 0, (size_t)batch * nblk * 4 * sizeof(int), st));
     const bool ahead = la && la->st2 && nblk >= 3 && lookahead_enabled();
+    // one launch per step only while all its CTAs are resident together (the row tiles wait on their SMs for the
+    // diagonal CTA); a wider batch takes the diagonal part and the row tiles as two launches
+    static const int sms = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
+    const bool split = (int64_t)batch * chol_step_ctas(n, nrows, 0) > sms;
+    auto step = [&](int J0, int prologue, cudaStream_t s) {
+        if (!split) {
+            launch_chol_step(A, ld, sA, n, nrows, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 0);
+            if (launches) ++*launches;
+        } else {
+            launch_chol_step(A, ld, sA, n, nrows, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 1);
+            launch_chol_step(A, ld, sA, n, nrows, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 2);
+            if (launches) *launches += 2;
+        }
+    };
     if (!ahead) {
         for (int J = 0; J < nblk; J++) {
             const int J0 = J * kDiag, Jend = std::min(n, J0 + kDiag), Jend2 = std::min(n, Jend + kDiag);
-            launch_chol_step(A, ld, sA, n, nrows, J0, steppub, logdet_part, nblk, stepsync, J > 0, batch, st);
-            if (launches) ++*launches;
+            step(J0, J > 0, st);
             potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend2, n, batch, st, launches, prof);
         }
         launch_trtri_diag(A, ld, sA, n, invd, sInvd, batch, st);
@@ -182,8 +200,7 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
     for (int J = 0; J < nblk; J++) {
         const int J0 = J * kDiag, Jend = std::min(n, J0 + kDiag), Jend2 = std::min(n, Jend + kDiag);
         if (J >= 2) CUGP_CUDA(cudaStreamWaitEvent(s2, evU(J - 2), 0));
-        launch_chol_step(A, ld, sA, n, nrows, J0, steppub, logdet_part, nblk, stepsync, J > 0, batch, s2);
-        if (launches) ++*launches;
+        step(J0, J > 0, s2);
         if (Jend2 >= n) continue;   // nothing right of block J+1
         CUGP_CUDA(cudaEventRecord(evP(J), s2));
         CUGP_CUDA(cudaStreamWaitEvent(st, evP(J), 0));
@@ -205,7 +222,8 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
     const int NB = potrf_outer_width(n);
     const int npanels = cdiv(n, NB);
     if (la) la->panel_events = false;
-    if (stepsync && steppub && g_fused_step && NB == kDiag) {
+    // (a batch wider than ~10 matrices is throughput bound: there the batched GEMM chain of round 1 is as fast)
+    if (stepsync && steppub && g_fused_step && NB == kDiag && batch <= g_fused_max_batch) {
         potrf_fused(A, ld, sA, n, nrows, invd, sInvd, logdet_part, nblk, batch, st, launches, prof, la, stepsync, steppub);
         return;
     }

@@ -138,6 +138,7 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
                    int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr, PotrfLookahead* la = nullptr,
                    int rhs_rows = 0, int* stepsync = nullptr, double* steppub = nullptr);
 void set_pred_chunk(int v); // > 0: cap on the test points one prediction chunk carries (0: by memory)
+void set_fused_max_batch(int v);   // widest batch the fused step is used for
 void set_fused_step(int v); // 1 (default): one fused launch per 128-column block step when the outer width is 128
 // Tuning epoch: bumped by every tuning change so cached graphs are re-captured.  graph_max_n: largest n whose launch
 // chains are replayed as CUDA graphs (0 disables).

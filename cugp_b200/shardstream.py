@@ -83,7 +83,8 @@ class ShardStream(BCM):
         self.offset = [i * int(numtrain) for i in range(int(numchunks))]
         self.log_hyper_bcm = np.zeros(3)
         self._local = local
-        self.exchanges = 0
+        self._in_library = False     # the stream's exchange step goes through torch.distributed (BCM._allreduce)
+        self._exchanges = 0
 
     @staticmethod
     def _rank_world(rank, world, group):
