@@ -162,6 +162,56 @@ def test_reference_bcm_driver_runs_on_the_shim():
     assert [f"{v:.6f}" for v in got] == [f"{v:.6f}" for v in th], (got, th)
 
 
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs (run under gpurun --gpus 2)")
+def test_reference_bcm_driver_runs_on_two_gpus_without_python():
+    """The same unchanged reference driver, started once per GPU with CUGP_RANK / CUGP_WORLD / CUGP_NCCL_ID_FILE: the shim's
+    BCM shards the 4 experts over the ranks and the LIBRARY allreduces (ncclAllReduce, no torch, no Python) -- every rank
+    must print the single-process optimum.  This is the socket master/worker layer of cuda_src/cg_solver.cpp:22-79
+    replaced at the reference's own call surface."""
+    exe = os.path.join(OUT, "distributed_ver1")
+    if not os.path.exists(exe):
+        pytest.skip("driver binary not built (needs the reference sources; built in the CPU container)")
+    from oracle import oracle
+    from tests.conftest import load_data
+    d = load_data("si128x2")
+    world = 2
+    with tempfile.TemporaryDirectory() as t:
+        os.makedirs(os.path.join(t, "dataset"))
+        os.makedirs(os.path.join(t, "run"))
+        with open(os.path.join(t, "dataset", "input_128.txt"), "w") as f:
+            f.write("128 2\n")
+            for row in d["X"]:
+                f.write(" ".join(repr(float(v)) for v in row) + "\n")
+        with open(os.path.join(t, "dataset", "label_128.txt"), "w") as f:
+            for v in d["y"]:
+                f.write(repr(float(v)) + "\n")
+        procs = []
+        for r in range(world):
+            env = dict(os.environ, LD_LIBRARY_PATH=LIBDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""), CUGP_RANK=str(r),
+                       CUGP_WORLD=str(world), CUGP_NCCL_ID_FILE=os.path.join(t, "nccl_id"))
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+                env.pop(k, None)
+            procs.append(subprocess.Popen([exe], cwd=os.path.join(t, "run"), env=env, stdout=subprocess.PIPE,
+                                          stderr=subprocess.PIPE, text=True))
+        outs = [p.communicate(timeout=600) for p in procs]
+    th, _, _ = oracle.port().cg_solve(d["X"], d["y"], [1.5, 1.5, 1.5], K=4)
+    for r, (p, (out, err)) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, (r, out[-1500:], err[-1500:])
+        finals = re.findall(r"PLEASE-SEE\s+3:\s*(\S+), (\S+), (\S+)", out)
+        assert finals, (r, out[-1500:], err[-1500:])
+        got = [float(v) for v in finals[-1]]
+        assert [f"{v:.6f}" for v in got] == [f"{v:.6f}" for v in th], (r, got, th)
+
+
 @pytest.mark.gpu
 def test_gpu_flavour_facade_reproduces_reference_logs():
     """cugp_shim/cuda_gp.h: setup / compute_log_likelihood / compute_gradient_log_hyperparams / set_loghyper_eigen /
