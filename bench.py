@@ -37,6 +37,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TH_B = [3.762111, -1.152105, -0.384461]   # trained values, cuda_src/main.cpp:191-193
+# The reference's CPU path cannot run the GPU sizes (n = 100 000 needs 560 GB of host buffers and ~10^5 core-hours), so
+# the CPU legs time it on the first REF_SAMPLE_N rows of the SAME synthetic set.  ONE size per workload, used by both the
+# `cpu_baseline` leg and `--impl reference`; every CPU line says so (`same_config: false`) -- a flop-rate or
+# evaluation-rate ratio across sizes is a stated baseline, not a like-for-like speed-up.
+REF_SAMPLE_N = {"c5": 2048, "c3": 2048, "c2": 1024, "c4": 1500}
 TH_C = [2.0, 2.0, 2.0]                    # cuda_scalingdist/main.cpp:298-301
 NOMINAL_FP64_TFLOPS = 37.0                # HGX B200 data sheet, dense FP64 (tensor = vector)
 
@@ -156,9 +161,31 @@ def cpu_baseline(kind_pref: str, n_s: int, theta, reps: int = 1):
         ll = impl.loglik(X, y, theta)
         dt = time.perf_counter() - t
         best = dt if best is None else min(best, dt)
-    return {"value": (n_s ** 3 / 3) / best / 1e12, "unit": "TFLOP/s", "cores": 1, "kind": impl.kind,
+    return {"value": (n_s ** 3 / 3) / best / 1e12, "unit": "TFLOP/s", "cores": 1, "kind": impl.kind, "same_config": False,
+            "sample_n": n_s,
             "sample": f"one compute_loglikelihood on the first {n_s} rows of the same synthetic set, theta_B, "
                       f"{best:.2f} s, LL={ll:.6f}; host has {os.cpu_count()} cores, reference is single-threaded"}
+
+
+def cpu_c4_model(impl, m: int, m_lo: int = 4, m_hi: int = 260):
+    """The reference's BCM prediction at the GPU arm's OWN m: every expert pays its training (three factorisations and
+    the inverse, covkernel.cpp:277-296) once and then O(n^2) per test point (covkernel.cpp:297-302).  Both parts are
+    timed on expert 0 (1500 rows): T(m_lo) and T(m_hi) give the per-point time and the training time; the ensemble
+    is 16 such experts in sequence (BCM.cpp:64-83), so pts/s = m / (16 (T_train + m t_point))."""
+    d4 = np.load(os.path.join(ROOT, "tests", "golden", "data_si24000.npz"))
+    Xt = np.load(os.path.join(ROOT, "tests", "golden", "data_c4_xtest600.npz"))["Xtest"]
+    X, y = d4["X"][:1500], d4["y"][:1500]
+    t = time.perf_counter()
+    impl.predict(X, y, TH_C, Xt[:m_lo])
+    t_lo = time.perf_counter() - t
+    t = time.perf_counter()
+    impl.predict(X, y, TH_C, Xt[:m_hi])
+    t_hi = time.perf_counter() - t
+    t_point = max((t_hi - t_lo) / (m_hi - m_lo), 1e-9)
+    t_train = max(t_lo - m_lo * t_point, 0.0)
+    return {"value": m / (16.0 * (t_train + m * t_point)), "t_train_s": t_train, "t_point_s": t_point,
+            "sample": f"expert 0 of 16 (1500 rows), theta_C: train {t_train:.2f} s + {1e3 * t_point:.2f} ms per test point "
+                      f"(from {m_lo} and {m_hi} points); ensemble = 16 experts in sequence at m = {m}"}
 
 
 def run_reference_arm(a):
@@ -169,9 +196,11 @@ def run_reference_arm(a):
     from cugp_b200.loaders import synthetic_sine
     from oracle import oracle
     impl = oracle.reference() or oracle.port()
-    n_s = {"c5": 1536, "c3": 1536, "c2": 1024, "c4": 1500}[a.workload]
-    X, y = synthetic_sine(n_s + 64, 10)
+    n_s = REF_SAMPLE_N[a.workload]
+    lohi = (-20.0, 20.0, 0.05) if a.workload == "c2" else (-10.0, 10.0, 0.1)
+    X, y = synthetic_sine(n_s + 64, 10, lo=lohi[0], hi=lohi[1], noise=lohi[2])
     Xt, X, y = X[n_s:], X[:n_s], y[:n_s]
+    model = []
 
     def step():
         if a.workload in ("c5", "c3"):
@@ -180,10 +209,11 @@ def run_reference_arm(a):
             impl.loglik(X, y, TH_B)
             impl.grad(X, y, TH_B)
         else:
-            impl.predict(X, y, TH_C, Xt)
+            model.append(cpu_c4_model(impl, a.m, 4, 68))
 
     for _ in range(a.warmup):
         step()
+    model.clear()
     t = time.perf_counter()
     for _ in range(a.steps):
         step()
@@ -191,16 +221,22 @@ def run_reference_arm(a):
     if a.workload in ("c5", "c3"):
         metric, unit, value = "fp64_cholesky_tflops", "TFLOP/s", (n_s ** 3 / 3) / (ms * 1e-3) / 1e12
         sample = f"compute_loglikelihood, n={n_s} synthetic rows (of {a.n}), theta_B"
+        same = False
     elif a.workload == "c2":
         metric, unit, value = "loglik_grad_evals_per_s", "evals/s", 1e3 / ms
         sample = f"compute_loglikelihood + compute_gradient_loghyperparam, n={n_s} (of 4096), theta_B"
+        same = False
     else:
-        metric, unit, value = "bcm_pred_pts_per_s", "pts/s", 64 / (ms * 1e-3)
-        sample = f"one expert (n={n_s}) predicting 64 points incl. its factorisation, theta_C"
+        metric, unit = "bcm_pred_pts_per_s", "pts/s"
+        value = statistics.median(mm["value"] for mm in model)
+        sample = model[-1]["sample"]
+        same = True
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": a.workload, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": unit, "cores": 1, "kind": impl.kind, "sample": sample},
+            "dtype": "f64", "data": "synthetic", "config": {"workload": a.workload, "sample": sample, "sample_n": n_s,
+                                                              "same_config": same},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": 1, "kind": impl.kind, "sample": sample, "sample_n": n_s,
+                             "same_config": same},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -241,7 +277,34 @@ def extra_c2(cg, torch, flush, n=4096, evals=6):
     return 1.0 / statistics.median(ts[2:])
 
 
-def extra_c4(cg, torch, dist, flush, m=10000, reps=4, experts=16, prefix="c4"):
+def bcm_parity(cg, torch, dist):
+    """Same-run parity of the sharded ensemble on EVERY rank: C4 (si24000, 16 experts, theta_C) against the golden values
+    generated from the unmodified reference (tests/golden/golden_c4.json) at the north-star tolerances."""
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_c4.json")))["cases"]["C4_si24000_bcm16_thC_pred16"]
+    d = np.load(os.path.join(ROOT, "tests", "golden", "data_si24000.npz"))
+    b = cg.BCM(d["X"], d["y"], K=16)
+    b.set_BCM_log_hyperparam(gold["theta"])
+    ll, g = b.loglik_and_gradient()
+    mu, var = b.compute_BCM_test_means_and_var(d["Xtest"][:gold["m"]])
+    in_lib = bool(getattr(b, "_in_library", False))
+    b.close()
+    gref = np.array(gold["grad"])
+    e = {"ll": abs(ll - gold["ll"]) / abs(gold["ll"]),
+         "grad": float(np.max(np.abs(g - gref) / np.maximum(np.abs(gref), 1e-3 * np.abs(gref).max()))),
+         "mean": float(np.max(np.abs(mu - gold["mean"]) / np.maximum(np.abs(gold["mean"]), 1e-6))),
+         "var": float(np.max(np.abs(var - gold["var"]) / np.abs(gold["var"])))}
+    ok = e["ll"] <= 1e-9 and e["grad"] <= 1e-9 and e["mean"] <= 1e-8 and e["var"] <= 1e-8
+    worst = [e["ll"], e["grad"], e["mean"], e["var"], 0.0 if ok else 1.0]
+    if dist is not None:
+        t = torch.tensor(worst, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)          # the WORST rank decides
+        worst = [float(v) for v in t.tolist()]
+    return {"parity_ok_all_ranks": worst[4] == 0.0, "golden": "tests/golden/golden_c4.json (unmodified reference)",
+            "max_rel_err_over_ranks": {"ll": worst[0], "grad": worst[1], "mean": worst[2], "var": worst[3]},
+            "tolerance": {"ll": 1e-9, "grad": 1e-9, "mean": 1e-8, "var": 1e-8}, "exchange_inside_library": in_lib}
+
+
+def extra_c4(cg, torch, dist, flush, m=10000, reps=6, experts=16, prefix="c4"):
     """BCM 16 x 1500 on ALL ranks of this run (experts e % world == rank, NCCL allreduce of the moments):
     prediction pts/s with factorised experts resident, and (LL, gradient) evaluations/s; theta_C.
     experts != 16: the same generator at `experts` x 1500 synthetic rows (an ensemble large enough that eight GPUs still
@@ -285,9 +348,55 @@ def extra_c4(cg, torch, dist, flush, m=10000, reps=4, experts=16, prefix="c4"):
 
     t_pred = timed(lambda: b.compute_BCM_test_means_and_var(Xt))
     t_eval = timed(ev)
+    world = b.world
     b.close()
     return {f"{prefix}_bcm_pred_pts_per_s": m / t_pred, f"{prefix}_bcm_loglik_grad_evals_per_s": 1.0 / t_eval,
-            f"{prefix}_gpus": b.world, f"{prefix}_test_points": m, f"{prefix}_experts_x_rows": f"{experts} x 1500"}
+            f"{prefix}_pred_ms": 1e3 * t_pred, f"{prefix}_eval_ms": 1e3 * t_eval,
+            f"{prefix}_gpus": world, f"{prefix}_test_points": m, f"{prefix}_experts_x_rows": f"{experts} x 1500"}
+
+
+def bcm_block(cg, torch, dist, flush, m=10000):
+    """The part of the metric that shards (BASELINE.json: 'BCM pred pts/s at 1-8 GPU'), measured on the ranks of THIS run:
+    C4 itself and the same shape at 64 experts, with the same-run parity flag."""
+    out = {"workload": "C4 BCM si24000 16 experts x 1500, theta_C; experts e % world per rank; ONE ncclAllReduce per "
+                       "operation (4 doubles per evaluation, 2 m doubles per prediction) issued by the library",
+           "timing": "median of 5 calls, max over ranks, host wall clock around the blocking call (device work + exchange + "
+                     "result copy), 256 MB L2 flush before every call"}
+    out["parity"] = bcm_parity(cg, torch, dist)
+    out.update(extra_c4(cg, torch, dist, flush, m=m))
+    out.update(extra_c4(cg, torch, dist, flush, m=m, experts=64, prefix="c4x4"))
+    return out
+
+
+def correctness_block(cg, L, X, y, n):
+    """Outside the timed region: is the factorisation of THIS size right?  (The reference printed a Cholesky residual
+    after every factorisation, cuda_src/cuda_gp.cu:1126-1139.)  residual: ||K alpha - y|| / ||y|| with K rebuilt matrix-free
+    (K itself was overwritten by L); logdet_crosscheck: log det K and y'K^-1 y from a second factorisation with another
+    outer block width and no look-ahead -- a different launch schedule and update order over the same kernels."""
+    g = cg.Covsum(n, 10)
+    g.set_data(X, y)
+    g.set_loghyperparam(TH_B)
+    q, ld, ll = g.scalars_resident()
+    r = g.residual_resident()
+    res = float(np.linalg.norm(r) / np.linalg.norm(y))
+    a = g.alpha_resident()
+    nb_default = 1024 if n >= 24576 else 512 if n >= 9000 else 256 if n >= 5000 else 128
+    nb_alt = 512 if nb_default != 512 else 256
+    try:
+        L.cugp_set_tuning(b"potrf_nb", nb_alt)
+        L.cugp_set_tuning(b"lookahead", 0)
+        g.factorize_resident()
+        q2, ld2, _ = g.scalars_resident()
+    finally:
+        L.cugp_set_tuning(b"potrf_nb", 0)
+        L.cugp_set_tuning(b"lookahead", 1)
+    g.close()
+    return {"n": n, "theta": TH_B, "c5_residual": res, "residual_bound": 1e-10,
+            "quad_vs_y_dot_alpha_rel": float(abs(q - y @ a) / abs(q)),
+            "c5_logdet_crosscheck": {"logdet": ld, "logdet_alt": ld2, "rel_diff": float(abs(ld - ld2) / abs(ld)),
+                                     "quad": q, "quad_alt": q2, "quad_rel_diff": float(abs(q - q2) / abs(q)),
+                                     "schedules": f"outer width {nb_default} + look-ahead vs outer width {nb_alt}, single stream"},
+            "ok": bool(res <= 1e-10 and abs(ld - ld2) <= 1e-11 * abs(ld) and abs(q - q2) <= 1e-10 * abs(q))}
 
 
 def extra_f3(cg, torch, dist, flush, chunks=32, n=2000, d=7, slots=8, passes=3):
@@ -480,17 +589,15 @@ def main():
         b.close()
         # the two halves of the step on their own: prediction with the factorised experts resident (the metric's name)
         # and the (LL, gradient) evaluation, each max-over-ranks
-        out["phases"] = extra_c4(cg, torch, dist, flush, m=a.m)
-        # the same ensemble shape at 64 experts (96 000 rows): eight GPUs still hold eight experts each
-        out["phases"].update(extra_c4(cg, torch, dist, flush, m=a.m, experts=64, prefix="c4x4"))
+        # (also at 64 experts -- 96 000 rows -- where eight GPUs still hold eight experts each), with the same-run parity flag
+        out["bcm"] = bcm_block(cg, torch, dist, flush, m=a.m)
 
     extra = None
     if not a.no_extra and a.workload == "c5":   # collective: every rank takes part in the sharded BCM
         try:
-            extra = extra_c4(cg, torch, dist, flush)
-            extra.update(extra_c4(cg, torch, dist, flush, experts=64, prefix="c4x4"))
+            out["bcm"] = bcm_block(cg, torch, dist, flush)
         except Exception as e:  # the headline must still print
-            extra = {"error": repr(e)}
+            out["bcm"] = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -529,6 +636,8 @@ def main():
                            "frac_of_nominal_37": achieved / NOMINAL_FP64_TFLOPS,
                            "launches_timed": syrk_cnt, "share_of_step": syrk_ms / ((a.steps + a.warmup) * ms),
                            "algorithmic_flops_per_launch": "m(m+1)*K for an m x m trailing block (lower triangle, 2 flop/MAC)"}
+    if a.workload in ("c5", "c3") and not a.no_extra:
+        out["correctness"] = correctness_block(cg, L, X, y, n)
     out["fp64_peaks_tflops"] = dict(fp64, cublas_dgemm_8192=cublas, nominal=NOMINAL_FP64_TFLOPS)
     out["hbm"] = {"copy_probe_gbs": copy_gbs, "peak_gbs": pk.get("hbm_gbs"), "peak_source": pk_src}
     if "phases_ms" in out and pk.get("hbm_gbs"):
@@ -545,7 +654,7 @@ def main():
         except Exception as e:
             extra["f3_error"] = repr(e)
         out["extra"] = extra
-    n_s = 2048 if a.workload in ("c5", "c3") else 1024
+    n_s = REF_SAMPLE_N[a.workload]
     skip_cpu = a.no_cpu or world != 1          # the CPU baseline is a rank-0, N = 1 leg
     if skip_cpu:
         cpu = {"value": None, "unit": None, "cores": 0, "kind": "skipped",
@@ -562,20 +671,15 @@ def main():
         impl.loglik(Xs, ys, TH_B)
         impl.grad(Xs, ys, TH_B)
         dt = time.perf_counter() - t
-        cpu = {"value": 1.0 / dt, "unit": "evals/s", "cores": 1, "kind": impl.kind,
+        cpu = {"value": 1.0 / dt, "unit": "evals/s", "cores": 1, "kind": impl.kind, "same_config": False, "sample_n": n_s,
                "sample": f"one LL + gradient at n={n_s} (of {n}), theta_B, {dt:.1f} s"}
     elif a.workload == "c4":
-        # bounded sample: ONE of the 16 experts (its factorisation, inverse and 8 predictions are 1/16 of the ensemble's
-        # sequential CPU work, BCM.cpp:64-83), scaled to the ensemble
+        # like for like with the GPU arm's m: training once per expert + m per-point costs (cpu_c4_model)
         from oracle import oracle
         impl = oracle.reference() or oracle.port()
-        d4 = np.load(os.path.join(ROOT, "tests", "golden", "data_si24000.npz"))
-        m_s = 8
-        t = time.perf_counter()
-        impl.predict(d4["X"][:1500], d4["y"][:1500], TH_C, d4["Xtest"][:m_s])
-        dt = time.perf_counter() - t
-        cpu = {"value": m_s / (16.0 * dt), "unit": "pts/s", "cores": 1, "kind": impl.kind,
-               "sample": f"expert 0 of 16 (1500 rows): train + predict {m_s} points, theta_C, {dt:.1f} s; ensemble = 16 x that"}
+        mod = cpu_c4_model(impl, a.m)
+        cpu = {"value": mod["value"], "unit": "pts/s", "cores": 1, "kind": impl.kind, "same_config": True, "sample_n": 1500,
+               "sample": mod["sample"], "t_train_s": mod["t_train_s"], "t_point_s": mod["t_point_s"]}
     line = {"metric": out.pop("metric"), "value": out.pop("value"), "unit": out.pop("unit"), "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": out.pop("ms_per_step"), "higher_is_better": True, "scaling": out.pop("scaling"),
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,

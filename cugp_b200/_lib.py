@@ -58,6 +58,7 @@ SIGNATURES = {
     "cugp_covsum_grad_resident": (C.c_int, [C.c_void_p, dp]),
     "cugp_covsum_scalars_resident": (C.c_int, [C.c_void_p, dp]),
     "cugp_covsum_alpha_resident": (C.c_int, [C.c_void_p, dp]),
+    "cugp_covsum_residual_resident": (C.c_int, [C.c_void_p, dp]),
     "cugp_covsum_factorize_resident": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "cugp_covsum_solve_resident": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cugp_covsum_profile": (C.c_int, [C.c_void_p, C.c_int]),

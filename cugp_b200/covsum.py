@@ -140,6 +140,12 @@ class Covsum:
         check(lib().cugp_covsum_alpha_resident(self._h, ptr(a)))
         return a
 
+    def residual_resident(self):
+        """r = (K + sn2 I) alpha - y, K rebuilt on the fly: ||r|| / ||y|| checks build + Cholesky + solves at any n."""
+        r = np.empty(self.inputdatasize)
+        check(lib().cugp_covsum_residual_resident(self._h, ptr(r)))
+        return r
+
     def factorize_resident(self):
         """Covariance build + Cholesky only; returns (ms_cov, ms_chol) measured with CUDA events."""
         a, b = C.c_float(), C.c_float()

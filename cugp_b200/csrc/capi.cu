@@ -344,6 +344,21 @@ int cugp_covsum_alpha_resident(cugp_covsum* h, double* alpha) {
     return CUGP_OK;
     CUGP_CATCH
 }
+// r = K alpha - y, with K rebuilt on the fly from X (it no longer exists: L overwrote it) and alpha = K^-1 y from the
+// factorisation.  ||r|| / ||y|| is the end-to-end check of build + Cholesky + both triangular solves at any n.
+int cugp_covsum_residual_resident(cugp_covsum* h, double* r_out) {
+    CUGP_TRY
+    if (int rc = need_data(h)) return rc;
+    if (!r_out) return CUGP_ERR_INVALID;
+    GpBatch& g = *h->gp;
+    g.solve();
+    launch_cov_residual(g.X, g.n, g.dp, g.h, g.alpha, g.y, g.work, g.st);   // `work` is free once alpha exists
+    g.launches++;
+    CUGP_CUDA(cudaMemcpyAsync(r_out, g.work, (size_t)g.n * 8, cudaMemcpyDeviceToHost, g.st));
+    g.sync();
+    return CUGP_OK;
+    CUGP_CATCH
+}
 int cugp_covsum_factorize_resident(cugp_covsum* h, float* ms_cov, float* ms_chol) {
     CUGP_TRY
     if (int rc = need_data(h)) return rc;

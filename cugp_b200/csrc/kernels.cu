@@ -303,6 +303,61 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const double* part, in
     }
 }
 
+// Matrix-free residual r = (K(X,X) + sn2 I) v - y for the correctness check of a factorisation whose K has already been
+// overwritten by L (bench.py `c5_residual`; the reference printed a residual after every factorisation,
+// cuda_src/cuda_gp.cu:1126-1139).  One CTA owns 64 rows and walks all column tiles, rebuilding K tile by tile with the
+// same arithmetic as K1; per-row sums are reduced in a fixed order.
+__global__ void __launch_bounds__(COV_THREADS) cov_matvec_kernel(const double* __restrict__ X, int n, int dp, Hyper h,
+                                                                 const double* __restrict__ v, const double* __restrict__ y,
+                                                                 double* __restrict__ r) {
+    extern __shared__ __align__(16) double smem[];
+    double* xt_i = smem;                 // [dp][64]
+    double* xt_j = smem + CT * dp;       // [dp][64]
+    double* vj = xt_j + CT * dp;         // [64]
+    double* red = vj + CT;               // [16][64]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.x * CT;
+    for (int e = tid; e < CT * dp; e += COV_THREADS) {
+        const int rr = e % CT, k = e / CT;
+        xt_i[k * CT + rr] = (i0 + rr < n) ? X[(int64_t)(i0 + rr) * dp + k] : 0.0;
+    }
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j0 = 0; j0 < n; j0 += CT) {
+        __syncthreads();
+        for (int e = tid; e < CT * dp; e += COV_THREADS) {
+            const int rr = e % CT, k = e / CT;
+            xt_j[k * CT + rr] = (j0 + rr < n) ? X[(int64_t)(j0 + rr) * dp + k] : 0.0;
+        }
+        if (tid < CT) vj[tid] = (j0 + tid < n) ? v[j0 + tid] : 0.0;
+        __syncthreads();
+        double d2[4][4];
+        micro_d2(xt_i, xt_j, dp, ty, tx, d2);
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int gi = i0 + ty * 4 + a;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int cj = tx * 2 + 32 * (c >> 1) + (c & 1), gj = j0 + cj;
+                if (gj < n) {
+                    double kv = se_kernel(d2[a][c], h);
+                    if (gi == gj) kv += h.sn2;
+                    acc[a] += kv * vj[cj];
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; a++) red[tx * CT + ty * 4 + a] = acc[a];
+    __syncthreads();
+    if (tid < CT && i0 + tid < n) {
+        double s = 0.0;
+#pragma unroll
+        for (int t = 0; t < 16; t++) s += red[t * CT + tid];
+        r[i0 + tid] = s - y[i0 + tid];
+    }
+}
+
 template <int MODE>
 void launch_cov(const CovArgs& a, int64_t tiles, int batch, cudaStream_t st) {
     size_t smem = (size_t)4 * CT * a.dp * sizeof(double);
@@ -1007,6 +1062,17 @@ void launch_cov_train(const double* X, int64_t sX, int n, int dp, Hyper h, doubl
     int64_t t = cdiv(n, CT);
     if (full) launch_cov<COV_FULL>(a, t * (t + 1) / 2, batch, st);
     else launch_cov<COV_LOWER>(a, t * (t + 1) / 2, batch, st);
+}
+
+void launch_cov_residual(const double* X, int n, int dp, Hyper h, const double* v, const double* y, double* r, cudaStream_t st) {
+    const size_t smem = (size_t)(2 * CT * dp + CT + 16 * CT) * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CUGP_CUDA(cudaFuncSetAttribute(cov_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    cov_matvec_kernel<<<cdiv(n, CT), COV_THREADS, smem, st>>>(X, n, dp, h, v, y, r);
+    CUGP_CUDA(cudaGetLastError());
 }
 
 void launch_cov_cross(const double* Xt, int m, const double* X, int64_t sX, int n, int dp, Hyper h, const double* alpha,

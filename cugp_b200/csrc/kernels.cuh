@@ -24,6 +24,8 @@ constexpr int kMaxDim = 64;    // padded input dimension limit of the shared-mem
 // full = 0: lower tiles only (feeds the factorisation); full = 1: both triangles (API a3).
 void launch_cov_train(const double* X, int64_t sX, int n, int dp, Hyper h, double* K, int64_t ld, int64_t sK,
                       int batch, int full, cudaStream_t st);
+// r = (K(X,X) + sn2 I) v - y without materialising K (single GP): the factorisation's correctness check
+void launch_cov_residual(const double* X, int n, int dp, Hyper h, const double* v, const double* y, double* r, cudaStream_t st);
 // ---- K5a: cross covariance Kstar[t][i] (covkernel.cpp:105-116) fused with mean partials
 // meanpart[tile_j][t] = sum over the tile's train columns of Kstar[t][i]*alpha[i].
 void launch_cov_cross(const double* Xt, int m, const double* X, int64_t sX, int n, int dp, Hyper h,

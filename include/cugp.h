@@ -106,6 +106,10 @@ int cugp_covsum_grad_resident(cugp_covsum *h, double grad[3]);
 int cugp_covsum_scalars_resident(cugp_covsum *h, double out3[3]);
 /* alpha = K^-1 y of the resident problem (n values) */
 int cugp_covsum_alpha_resident(cugp_covsum *h, double *alpha);
+/* End-to-end check of a factorisation at any n (the reference printed a residual after every factorisation,
+ * cuda_src/cuda_gp.cu:1126-1139): r = (K(X,X) + sn2 I) alpha - y with K rebuilt tile by tile from X (K itself was
+ * overwritten by L) and alpha = K^-1 y from the Cholesky factor.  r_out: n doubles. */
+int cugp_covsum_residual_resident(cugp_covsum *h, double *r_out);
 /* Factorise only: covariance build, then the Cholesky with y appended as an extra row (which yields z = L^-1 y,
  * y'K^-1 y = z'z, log det and LL without a forward sweep); *ms_chol = device time of that second part (CUDA events
  * on the launching stream), for the FP64 roofline (n^3/3 flop). */

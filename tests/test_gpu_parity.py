@@ -488,3 +488,64 @@ def test_c3_size_properties():
     kst = np.stack([PORT.k_test(X, TH_B, x) for x in Xt])
     v = sl.solve_triangular(Lk, kst.T, lower=True)
     assert_pred(mu, var, kst @ a, sf2 + sn2 - (v * v).sum(0), yscale=1.0, rtol=1e-8)
+
+
+def test_residual_beyond_int32_indexing():
+    """n = 50 000 > 46 341: n * n no longer fits a 32-bit int -- where the reference's GPU flavour indexes with `int`
+    (cuda_src/cuda_gp.cu:613-642).  The reference printed a Cholesky residual after every factorisation
+    (cuda_src/cuda_gp.cu:1126-1139); here: ||K alpha - y|| / ||y|| with K rebuilt matrix-free, and the log-determinant and
+    y' K^-1 y must not depend on the outer block width or on the look-ahead."""
+    from cugp_b200.loaders import synthetic_sine
+    n = 50000
+    X, y = synthetic_sine(n, 10)
+    g = cg.Covsum(n, 10)
+    g.set_data(X, y)
+    g.set_loghyperparam(TH_B)
+    q, ld, ll = g.scalars_resident()
+    r = g.residual_resident()
+    assert np.linalg.norm(r) <= 1e-10 * np.linalg.norm(y), np.linalg.norm(r) / np.linalg.norm(y)
+    a = g.alpha_resident()
+    assert abs(q - y @ a) <= 1e-10 * abs(q)
+    assert ll == -0.5 * (q + ld + n * 1.83787)
+    try:
+        for nb, la in ((512, 1), (1024, 0)):
+            lib().cugp_set_tuning(b"potrf_nb", nb)
+            lib().cugp_set_tuning(b"lookahead", la)
+            g.set_loghyperparam([TH_B[0], TH_B[1], TH_B[2] + 0.0])   # same theta: force a fresh factorisation below
+            g.factorize_resident()
+            q2, ld2, _ = g.scalars_resident()
+            assert abs(ld2 - ld) <= 1e-12 * abs(ld) and abs(q2 - q) <= 1e-11 * abs(q), (nb, la, ld, ld2, q, q2)
+    finally:
+        lib().cugp_set_tuning(b"potrf_nb", 0)
+        lib().cugp_set_tuning(b"lookahead", 1)
+    g.close()
+
+
+def test_cholesky_against_cusolver_at_40000():
+    """Test-only library cross-check (never on the product path): torch.linalg.cholesky (cuSOLVER) on the same K at
+    n = 40 000 -- log-determinant, y' K^-1 y and a sample of L."""
+    import torch
+    from cugp_b200.loaders import synthetic_sine
+    n = 40000
+    X, y = synthetic_sine(n, 10)
+    g = cg.Covsum(n, 10)
+    g.set_data(X, y)
+    g.set_loghyperparam(TH_B)
+    q, ld, _ = g.scalars_resident()
+    a = g.alpha_resident()
+    g.close()
+    del g
+    Xd = torch.from_numpy(X).cuda()
+    ell2, sf2, sn2 = np.exp(2 * TH_B[0]), np.exp(2 * TH_B[1]), np.exp(2 * TH_B[2])
+    K = torch.cdist(Xd, Xd).pow_(2).mul_(-0.5 / ell2).exp_().mul_(sf2)
+    K.diagonal().add_(sn2)
+    Lc = torch.linalg.cholesky(K)
+    del K
+    ld_ref = 2.0 * torch.log(Lc.diagonal()).sum().item()
+    yd = torch.from_numpy(y).cuda()
+    a_ref = torch.cholesky_solve(yd[:, None], Lc)[:, 0]
+    q_ref = float(yd @ a_ref)
+    # cdist's |x-y|^2 differs from the reference's ordered sum in the last bits: cond(K) ~ 2e4 amplifies that to ~1e-11
+    assert abs(ld - ld_ref) <= 1e-9 * abs(ld_ref), (ld, ld_ref)
+    assert abs(q - q_ref) <= 1e-8 * abs(q_ref), (q, q_ref)
+    assert np.linalg.norm(a - a_ref.cpu().numpy()) <= 1e-6 * np.linalg.norm(a)
