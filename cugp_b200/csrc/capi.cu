@@ -84,10 +84,10 @@ void untrack(GpBatch* g) {
 static void upload(cugp_covsum* h, const double* X, const double* y) {
     const size_t nx = (size_t)h->n * h->d, ny = (size_t)h->n;
     const bool same = h->have_host && std::memcmp(h->Xh.data(), X, nx * 8) == 0 && std::memcmp(h->yh.data(), y, ny * 8) == 0;
-    const bool hL = h->gp->have_L, hA = h->gp->have_alpha, hT = h->gp->have_T, hK = h->gp->have_Kinv;
+    const bool hL = h->gp->have_L, hA = h->gp->have_alpha, hT = h->gp->have_T, hK = h->gp->have_Kinv, hU = h->gp->have_Tt;
     h->gp->set_data(X, y);
     if (same) {
-        h->gp->have_L = hL; h->gp->have_alpha = hA; h->gp->have_T = hT; h->gp->have_Kinv = hK;
+        h->gp->have_L = hL; h->gp->have_alpha = hA; h->gp->have_T = hT; h->gp->have_Kinv = hK; h->gp->have_Tt = hU;
     } else {
         h->Xh.assign(X, X + nx);
         h->yh.assign(y, y + ny);
@@ -147,6 +147,11 @@ int cugp_set_tuning(const char* key, long value) {
     if (std::strcmp(key, "pred_chunk") == 0) {
         if (value < 0) return CUGP_ERR_INVALID;
         set_pred_chunk((int)value);
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "idrows_max_n") == 0) {   // takes effect for handles created afterwards (buffer size)
+        if (value < 0) return CUGP_ERR_INVALID;
+        set_idrows_max_n((int)value);
         return CUGP_OK;
     }
     if (std::strcmp(key, "fused_max_batch") == 0) {

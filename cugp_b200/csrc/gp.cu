@@ -68,6 +68,12 @@ bool lookahead_enabled() { return g_lookahead != 0; }
 static int g_fused_step = 1, g_fused_max_batch = 10;
 void set_fused_step(int v) { g_fused_step = v; bump_tuning_epoch(); }
 void set_fused_max_batch(int v) { g_fused_max_batch = v; bump_tuning_epoch(); }
+// Identity rows: for small n the factorisation carries n more appended rows that start as I and end as L^-T -- the inverse
+// of the factor costs no launch chain of its own (the TRTRI recursion is 12 dependent launches, 310 us at n = 1500 against
+// 420 us for the factorisation itself).  The row tiles of the fused step do the extra work in the diagonal CTA's shadow.
+static int g_idrows_max_n = 2048;
+void set_idrows_max_n(int n) { g_idrows_max_n = n; bump_tuning_epoch(); }
+int idrows_max_n() { return g_idrows_max_n; }
 static int g_potrf_nb = 0;  // 0: by size; otherwise forced (cugp_set_tuning("potrf_nb", v) or CUGP_POTRF_NB)
 void set_potrf_outer_width(int nb) { g_potrf_nb = nb; bump_tuning_epoch(); }
 int potrf_outer_width(int n) {
@@ -83,6 +89,10 @@ int potrf_outer_width(int n) {
     if (n >= 9000) return 512;
     if (n >= 5000) return 256;
     return kDiag;
+}
+
+bool fused_step_applies(int n, int batch) {
+    return g_fused_step && potrf_outer_width(n) == kDiag && batch <= g_fused_max_batch;
 }
 
 // One outer panel [J0, Jend): right-looking over its 128-column blocks, full height, updates confined to the panel.
@@ -155,7 +165,7 @@ static void potrf_trailing(double* A, int64_t ld, int64_t sA, int nrows, int J0,
 // Both step(J+2) and U2(J) touch block column J+2: step(J+2) waits for U2(J).
 static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, double* invd, int64_t sInvd, double* logdet_part,
                         int nblk, int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la,
-                        int* stepsync, double* steppub) {
+                        int* stepsync, double* steppub, int id_rows) {
     CUGP_CUDA(cudaMemsetAsync(stepsync, 0, (size_t)batch * nblk * 4 * sizeof(int), st));
     const bool ahead = la && la->st2 && nblk >= 3 && lookahead_enabled();
     // one launch per step only while all its CTAs are resident together (the row tiles wait on their SMs for the
@@ -165,14 +175,21 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
         return v > 0 ? v : 148;
     }();
-    const bool split = (int64_t)batch * chol_step_ctas(n, nrows, 0) > sms;
+    // The last id_rows appended rows are the identity: row i of it is zero left of column i, so at the step of block
+    // column J only its first Jend rows take part -- in the step itself and in the trailing update of panel J.
+    const int base_rows = nrows - id_rows;
+    auto rows_at = [&](int Jend) { return base_rows + std::min(id_rows, Jend); };
+    int widest = 0;
+    for (int J0 = 0; J0 < n; J0 += kDiag) widest = std::max(widest, chol_step_ctas(n, rows_at(std::min(n, J0 + kDiag)), J0));
+    const bool split = (int64_t)batch * widest > sms;
     auto step = [&](int J0, int prologue, cudaStream_t s) {
+        const int nr = rows_at(std::min(n, J0 + kDiag));
         if (!split) {
-            launch_chol_step(A, ld, sA, n, nrows, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 0);
+            launch_chol_step(A, ld, sA, n, nr, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 0);
             if (launches) ++*launches;
         } else {
-            launch_chol_step(A, ld, sA, n, nrows, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 1);
-            launch_chol_step(A, ld, sA, n, nrows, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 2);
+            launch_chol_step(A, ld, sA, n, nr, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 1);
+            launch_chol_step(A, ld, sA, n, nr, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 2);
             if (launches) *launches += 2;
         }
     };
@@ -180,7 +197,7 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
         for (int J = 0; J < nblk; J++) {
             const int J0 = J * kDiag, Jend = std::min(n, J0 + kDiag), Jend2 = std::min(n, Jend + kDiag);
             step(J0, J > 0, st);
-            potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend2, n, batch, st, launches, prof);
+            potrf_trailing(A, ld, sA, rows_at(Jend), J0, Jend, Jend2, n, batch, st, launches, prof);
         }
         launch_trtri_diag(A, ld, sA, n, invd, sInvd, batch, st);
         if (launches) ++*launches;
@@ -204,7 +221,7 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
         if (Jend2 >= n) continue;   // nothing right of block J+1
         CUGP_CUDA(cudaEventRecord(evP(J), s2));
         CUGP_CUDA(cudaStreamWaitEvent(st, evP(J), 0));
-        potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend2, n, batch, st, launches, prof);   // U2(J)
+        potrf_trailing(A, ld, sA, rows_at(Jend), J0, Jend, Jend2, n, batch, st, launches, prof);   // U2(J)
         CUGP_CUDA(cudaEventRecord(evU(J), st));
     }
     launch_trtri_diag(A, ld, sA, n, invd, sInvd, batch, s2);   // off-diagonal 32x32 blocks of the 128x128 inverses
@@ -215,7 +232,7 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
 
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part, int batch,
                    cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la, int rhs_rows, int* stepsync,
-                   double* steppub) {
+                   double* steppub, int id_rows) {
     if (prof && !prof->on) prof = nullptr;
     const int nrows = n + rhs_rows;
     const int nblk = cdiv(n, kDiag);
@@ -224,9 +241,10 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
     if (la) la->panel_events = false;
     // (a batch wider than ~10 matrices is throughput bound: there the batched GEMM chain of round 1 is as fast)
     if (stepsync && steppub && g_fused_step && NB == kDiag && batch <= g_fused_max_batch) {
-        potrf_fused(A, ld, sA, n, nrows, invd, sInvd, logdet_part, nblk, batch, st, launches, prof, la, stepsync, steppub);
+        potrf_fused(A, ld, sA, n, nrows, invd, sInvd, logdet_part, nblk, batch, st, launches, prof, la, stepsync, steppub, id_rows);
         return;
     }
+    if (id_rows) throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};   // identity rows exist on the fused path only
     if (!la || !la->st2 || npanels < 3 || !lookahead_enabled()) {
         for (int J0 = 0; J0 < n; J0 += NB) {
             const int Jend = std::min(n, J0 + NB);
@@ -344,7 +362,8 @@ GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(
     const size_t bn = (size_t)B * n;
     dalloc(X, bn * dp);
     dalloc(y, bn);
-    dalloc(Kb, (size_t)B * (n + 1) * ld);  // row n of every matrix: y^T, then z^T = (L^-1 y)^T
+    rows_alloc = n <= g_idrows_max_n ? 2 * n + 1 : n + 1;
+    dalloc(Kb, (size_t)B * rows_alloc * ld);  // row n of every matrix: y^T, then z^T = (L^-1 y)^T; rows n+1..: I -> L^-T
     dalloc(invd, (size_t)B * nblk * kDiag * kDiag);
     CUGP_CUDA(cudaMemsetAsync(invd, 0, (size_t)B * nblk * kDiag * kDiag * sizeof(double), st));  // upper triangles stay zero
     dalloc(logdet_part, (size_t)B * nblk);
@@ -367,7 +386,7 @@ GpBatch::~GpBatch() {
     for (cudaEvent_t e : prof.ev) cudaEventDestroy(e);
     for (cudaEvent_t e : la.ev) cudaEventDestroy(e);
     for (cudaEvent_t e : bwd_ev) cudaEventDestroy(e);
-    for (auto* cache : {&graph_potrf, &graph_potrf_rhs, &graph_inv})
+    for (auto* cache : {&graph_potrf, &graph_potrf_rhs, &graph_potrf_id, &graph_inv, &graph_inv_id})
         for (auto& kv : *cache)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (la.st2) {
@@ -525,15 +544,23 @@ void GpBatch::potrf(bool with_rhs) {
 // Cholesky of the matrix in Kb with y appended as row n: L in place, z = L^-1 y in row n, then
 // (quad = z'z = y'K^-1 y, logdet, LL) -- matrixops.cpp:113-185 + covkernel.cpp:127 without a separate forward sweep.
 void GpBatch::potrf_with_rhs() {
+    // A batch that has needed the inverse of its factor before gets it from the factorisation itself: n more appended
+    // rows that start as I and leave as L^-T (small n, fused step path only).
+    const bool id = wants_inverse && n <= g_idrows_max_n && rows_alloc >= 2 * n + 1 && fused_step_applies(n, B) && !prof.on;
     auto body = [&] {
         launch_copy_rows(y, n, Kb + (int64_t)n * ld, mat_stride(), n, B, st);
-        potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la, 1,
-                      stepsync, steppub);
+        if (id) {
+            launch_init_identity(Tt(), ld, mat_stride(), n, B, st);
+            launches++;
+        }
+        potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la,
+                      id ? 1 + n : 1, stepsync, steppub, id ? n : 0);
         const double* zrow = Kb + (int64_t)n * ld;
         launch_ll_finalize(zrow, zrow, mat_stride(), n, logdet_part, nblk, scal, B, st);
         launches += 2;
     };
-    if (!run_graphed(graph_potrf_rhs, body)) body();
+    if (!run_graphed(id ? graph_potrf_id : graph_potrf_rhs, body)) body();
+    have_Tt = id;
 }
 
 void GpBatch::prof_begin() {
@@ -621,7 +648,7 @@ void GpBatch::factorize() {
     potrf_with_rhs();
     have_L = true;
     // a batch that has computed gradients / predictions before (T exists) will want T = L^-1 again: start it now
-    if (Tb && Wb && la.panel_events && n <= g_overlap_max_n) enqueue_trtri_overlapped();
+    if (Tb && Wb && la.panel_events && !have_Tt && n <= g_overlap_max_n) enqueue_trtri_overlapped();
 }
 
 // alpha = L^-T z.  With T = L^-1 at hand (gradient / prediction paths) it is one streaming pass alpha = T^T z;
@@ -630,7 +657,10 @@ void GpBatch::solve() {
     if (have_alpha) return;
     factorize();
     const double* zrow = Kb + (int64_t)n * ld;
-    if (have_T) {
+    if (have_Tt) {
+        launch_gemv_upper(Tt(), ld, mat_stride(), n, zrow, mat_stride(), alpha, n, B, st);   // alpha = L^-T z
+        launches++;
+    } else if (have_T) {
         launch_gemv_t(Tb, ld, mat_stride(), n, zrow, mat_stride(), alpha, n, tpart, B, st);
         launches += 2;
     } else {
@@ -650,11 +680,12 @@ void GpBatch::solve() {
 }
 
 void GpBatch::ensure_TW() {
-    dalloc(Tb, (size_t)Bcap * (n + 1) * ld);  // same batch stride as Kb
-    dalloc(Wb, (size_t)Bcap * (n + 1) * ld);
+    dalloc(Tb, (size_t)Bcap * rows_alloc * ld);  // same batch stride as Kb
+    dalloc(Wb, (size_t)Bcap * rows_alloc * ld);
 }
 
 void GpBatch::trtri() {
+    wants_inverse = true;
     if (have_T) return;
     factorize();
     if (t_valid) {   // computed alongside the factorisation
@@ -673,6 +704,23 @@ void GpBatch::trtri() {
 
 void GpBatch::lauum() {
     if (have_Kinv) return;
+    factorize();
+    if (have_Tt) {
+        ensure_TW();
+        GemmParams p{};  // Kinv = U U^T with U = L^-T upper triangular, row-major: k >= max(i, j) = row-tile start (lower tiles)
+        p.A = Tt(); p.lda = ld; p.sA = mat_stride();
+        p.B = Tt(); p.ldb = ld; p.sB = mat_stride();
+        p.C = Wb; p.ldc = ld; p.sC = mat_stride();
+        p.M = n; p.N = n; p.K = n;
+        p.alpha = 1.0; p.beta = 0.0;
+        p.batch = B;
+        p.lower_tiles = 1;
+        p.klo_ti = 1;
+        launch_gemm(p, true, true, pick_config(n, n, B, true), st);
+        launches++;
+        have_Kinv = true;
+        return;
+    }
     trtri();
     GemmParams p{};  // Kinv = T^T T: k >= max(i,j) = row-tile start on the lower tile set
     p.A = Tb; p.lda = ld; p.sA = mat_stride();
@@ -701,21 +749,37 @@ void GpBatch::loglik(double* ll_out) {
 }
 
 void GpBatch::gradient_launch() {
+    wants_inverse = true;
     factorize();
-    if (!have_T && !have_alpha && !have_Kinv) {
-        // the whole inverse chain (TRTRI recursion, alpha = T^T z, LAUUM) is theta independent: one graph replay
-        ensure_TW();
-        auto body = [&] {
-            have_T = have_alpha = have_Kinv = false;
-            trtri();   // before solve(): alpha then is a single pass over T
+    if (have_Tt) {
+        // L^-T came out of the factorisation: alpha = L^-T z and K^-1 = L^-T L^-1 are two launches
+        if (!have_alpha || !have_Kinv) {
+            ensure_TW();
+            auto body = [&] {
+                have_alpha = have_Kinv = false;
+                solve();
+                lauum();
+            };
+            if (run_graphed(graph_inv_id, body)) have_alpha = have_Kinv = true;
             solve();
             lauum();
-        };
-        if (run_graphed(graph_inv, body)) have_T = have_alpha = have_Kinv = true;
+        }
+    } else {
+        if (!have_T && !have_alpha && !have_Kinv) {
+            // the whole inverse chain (TRTRI recursion, alpha = T^T z, LAUUM) is theta independent: one graph replay
+            ensure_TW();
+            auto body = [&] {
+                have_T = have_alpha = have_Kinv = false;
+                trtri();   // before solve(): alpha then is a single pass over T
+                solve();
+                lauum();
+            };
+            if (run_graphed(graph_inv, body)) have_T = have_alpha = have_Kinv = true;
+        }
+        trtri();
+        solve();
+        lauum();
     }
-    trtri();
-    solve();
-    lauum();
     dalloc(gradpart, grad_trace_partials(n, Bcap));
     launch_grad_trace(X, (int64_t)n * dp, n, dp, h, Wb, ld, mat_stride(), alpha, n, gradpart, gradout, B, st);
     launches += 2;
@@ -753,7 +817,9 @@ void GpBatch::ensure_pred(int mc) {
 // product-of-experts moments (may be null).  Nothing here waits for the device unless host outputs were asked for.
 void GpBatch::predict_dev(const double* Xt_dev, int m, double* mean_h, double* var_h, double* PQ_dev, int accumulate) {
     if (m <= 0) return;
-    trtri();
+    wants_inverse = true;
+    factorize();
+    if (!have_Tt) trtri();
     solve();
     // chunk the test set so Kstar stays near 2 GB
     int64_t cap = (int64_t)(2.0e9 / ((double)Bcap * ld * 8.0));
@@ -766,7 +832,7 @@ void GpBatch::predict_dev(const double* Xt_dev, int m, double* mean_h, double* v
         launch_cov_cross(Xt_dev + (size_t)t0 * dp, cur, X, (int64_t)n * dp, n, dp, h, alpha, n, Ks, ld, (int64_t)mc * ld, meanpart,
                          (int64_t)tiles_j * mc, B, st);
         GemmParams p{};  // V = T Kstar^T ; only the column sums of squares are kept
-        p.A = Tb; p.lda = ld; p.sA = mat_stride();
+        p.A = have_Tt ? Tt() : Tb; p.lda = ld; p.sA = mat_stride();   // T (rows) or T^T = L^-T (rows): same product
         p.B = Ks; p.ldb = ld; p.sB = (int64_t)mc * ld;
         p.M = n; p.N = cur; p.K = n;
         p.alpha = 1.0; p.beta = 0.0;
@@ -776,7 +842,7 @@ void GpBatch::predict_dev(const double* Xt_dev, int m, double* mean_h, double* v
         const GemmConfig cfg = pick_config(n, cur, B, false);
         const int tiles_m = cdiv(n, gemm_tile_m(cfg));
         p.sCss = (int64_t)tiles_m * cur;
-        launch_gemm(p, true, true, cfg, st);
+        launch_gemm(p, !have_Tt, true, cfg, st);
         // meanpart was written with row length `cur` (ni) and batch stride tiles_j*mc
         launch_predict_finalize(meanpart, tiles_j, css, tiles_m, cur, h, pmean, pvar, mc, (int64_t)tiles_j * mc, p.sCss,
                                 B, st);

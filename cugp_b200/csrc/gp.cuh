@@ -52,6 +52,8 @@ struct GpBatch {
     double theta[3] = {0, 0, 0};
     Hyper h{};
     bool have_data = false, have_L = false, have_alpha = false, have_T = false, have_Kinv = false;
+    bool have_Tt = false;       // rows n+1..2n of Kb hold L^-T (the identity rode through the factorisation)
+    bool wants_inverse = false; // this batch has asked for a gradient / prediction before: factorise with the identity rows
     long launches = 0;  // kernels launched since the last reset (bench.py `gpu_launches`)
     // optional timing of the dominant kernel (SYRK trailing update) with CUDA events on the launching stream
     struct Prof {
@@ -79,7 +81,7 @@ struct GpBatch {
         int uses = 0;        // direct runs before the capture (the first one configures kernel attributes, creates events)
         bool failed = false;
     };
-    std::map<int, GraphEntry> graph_potrf, graph_potrf_rhs, graph_inv;
+    std::map<int, GraphEntry> graph_potrf, graph_potrf_rhs, graph_potrf_id, graph_inv, graph_inv_id;
     template <class F>
     bool run_graphed(std::map<int, GraphEntry>& cache, F&& body);   // false: caller runs `body` directly
     void prof_begin();                     // reset counters (events are reused)
@@ -106,7 +108,7 @@ struct GpBatch {
     // an inverse still running on the third stream, then the cached state is dropped.
     void invalidate() {
         join_T();
-        have_L = have_alpha = have_T = have_Kinv = t_valid = false;
+        have_L = have_alpha = have_T = have_Kinv = have_Tt = t_valid = false;
     }
 
     void build_K(int full);                 // K1 into Kb
@@ -127,7 +129,11 @@ struct GpBatch {
 
     void sync() { CUGP_CUDA(cudaStreamSynchronize(st)); }
     void* stage(size_t bytes);
-    int64_t mat_stride() const { return (int64_t)(n + 1) * ld; }  // n rows + the appended right-hand-side row
+    // rows every matrix buffer holds: n + the appended right-hand-side row, and for small n another n rows below that
+    // which start as the identity and leave the factorisation as L^-T (see potrf_with_rhs)
+    int rows_alloc = 0;
+    int64_t mat_stride() const { return (int64_t)rows_alloc * ld; }
+    double* Tt() const { return Kb + (int64_t)(n + 1) * ld; }   // L^-T (upper triangular, row-major) when have_Tt
     void ensure_TW();
     void ensure_pred(int mc);
 };
@@ -136,7 +142,11 @@ struct GpBatch {
 // 128x128 diagonal blocks and per-block log-determinant partials as by-products.
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part,
                    int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr, PotrfLookahead* la = nullptr,
-                   int rhs_rows = 0, int* stepsync = nullptr, double* steppub = nullptr);
+                   int rhs_rows = 0, int* stepsync = nullptr, double* steppub = nullptr, int id_rows = 0);
+// true: an n x n factorisation of `batch` matrices takes the fused block-step path (outer width 128, batch small enough)
+bool fused_step_applies(int n, int batch);
+void set_idrows_max_n(int n);   // largest n whose factorisation carries the identity rows (0: never)
+int idrows_max_n();
 void set_pred_chunk(int v); // > 0: cap on the test points one prediction chunk carries (0: by memory)
 void set_fused_max_batch(int v);   // widest batch the fused step is used for
 void set_fused_step(int v); // 1 (default): one fused launch per 128-column block step when the outer width is 128

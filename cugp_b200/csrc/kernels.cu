@@ -942,6 +942,32 @@ __global__ void gemv_t_reduce_kernel(const double* partial, int64_t sPart, int n
     alpha[(int64_t)blockIdx.y * sAlpha + c] = s;
 }
 
+__global__ void init_identity_kernel(double* R, int64_t ld, int64_t sR, int n) {
+    const int64_t b = blockIdx.z;
+    const int i = blockIdx.y;
+    double2* row = reinterpret_cast<double2*>(R + b * sR + (int64_t)i * ld);
+    for (int c2 = blockIdx.x * blockDim.x + threadIdx.x; c2 < ld / 2; c2 += gridDim.x * blockDim.x)
+        row[c2] = make_double2(2 * c2 == i ? 1.0 : 0.0, 2 * c2 + 1 == i ? 1.0 : 0.0);
+}
+
+__global__ void __launch_bounds__(256) gemv_upper_kernel(const double* __restrict__ U, int64_t ld, int64_t sU, int n,
+                                                         const double* __restrict__ z, int64_t sZ, double* alpha, int64_t sAlpha) {
+    const int64_t b = blockIdx.y;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const double* row = U + b * sU + (int64_t)i * ld;
+    const double* zz = z + b * sZ;
+    double s = 0.0;
+    for (int k = (i & ~1) + 2 * lane; k < n; k += 64) {   // 16-byte loads from the even column at or before the diagonal
+        const double2 u = *reinterpret_cast<const double2*>(row + k);
+        if (k >= i) s += u.x * zz[k];
+        if (k + 1 < n) s += u.y * zz[k + 1];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) alpha[b * sAlpha + i] = s;
+}
+
 // dst[b][0..n) = src[b][0..n) with independent batch strides (y -> row n of the matrix, z -> work vector)
 __global__ void copy_rows_kernel(const double* src, int64_t sSrc, double* dst, int64_t sDst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1251,6 +1277,19 @@ void launch_gemv_t(const double* T, int64_t ld, int64_t sT, int n, const double*
     const int64_t sPart = (int64_t)GT_CHUNKS * n;     // == trsv_backward_scratch(n, 1)
     gemv_t_kernel<<<dim3(nblk, chunks, batch), TRSV_THREADS, 0, st>>>(T, ld, sT, n, rpc, z, sZ, scratch, sPart);
     gemv_t_reduce_kernel<<<dim3(cdiv(n, 256), batch), 256, 0, st>>>(scratch, sPart, n, rpc, alpha, sAlpha);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_init_identity(double* R, int64_t ld, int64_t sR, int n, int batch, cudaStream_t st) {
+    if (n <= 0 || batch <= 0) return;
+    init_identity_kernel<<<dim3(cdiv(ld / 2, 256), n, batch), 256, 0, st>>>(R, ld, sR, n);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_gemv_upper(const double* U, int64_t ld, int64_t sU, int n, const double* z, int64_t sZ, double* alpha, int64_t sAlpha,
+                       int batch, cudaStream_t st) {
+    if (n <= 0 || batch <= 0) return;
+    gemv_upper_kernel<<<dim3(cdiv(n, 8), batch), 256, 0, st>>>(U, ld, sU, n, z, sZ, alpha, sAlpha);
     CUGP_CUDA(cudaGetLastError());
 }
 

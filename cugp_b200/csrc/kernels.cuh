@@ -64,6 +64,11 @@ size_t trsv_backward_scratch(int n, int batch);  // doubles needed in `scratch`
 // alpha = T^T z with T = L^-1 lower triangular: one streaming pass (used whenever T exists)
 void launch_gemv_t(const double* T, int64_t ld, int64_t sT, int n, const double* z, int64_t sZ, double* alpha, int64_t sAlpha,
                    double* scratch /* trsv_backward_scratch(n, batch) doubles */, int batch, cudaStream_t st);
+// rows [0, n) of R (row stride ld, batch stride sR) <- identity (every entry of the n x ld block is written)
+void launch_init_identity(double* R, int64_t ld, int64_t sR, int n, int batch, cudaStream_t st);
+// alpha[i] = sum_{k >= i} U[i][k] z[k] for an upper-triangular row-major U (= L^-T): one warp per row, coalesced
+void launch_gemv_upper(const double* U, int64_t ld, int64_t sU, int n, const double* z, int64_t sZ, double* alpha, int64_t sAlpha,
+                       int batch, cudaStream_t st);
 void launch_copy_rows(const double* src, int64_t sSrc, double* dst, int64_t sDst, int n, int batch, cudaStream_t st);
 // scal[batch][4] = (u'v, logdet, LL, 0) for vectors u, v (u = v = z: quad = z'z = y'K^-1 y) with LL = -0.5*(quad + logdet + n*1.83787) (covkernel.cpp:127)
 void launch_ll_finalize(const double* y, const double* alpha, int64_t sVec, int n, const double* logdet_part,

@@ -297,7 +297,8 @@ static int open_common(int numchunks, int numtrain, int dim, int rank, int world
         // fit in 60 % of the free device memory, capped at 64 experts per launch.
         size_t free_b = 0, total_b = 0;
         CUGP_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const double per = 3.0 * (double)(numtrain + 1) * (double)padded_ld(numtrain) * 8.0 + 64.0 * 1024.0 * 1024.0;
+        const double rows = numtrain <= idrows_max_n() ? 2.0 * numtrain + 1.0 : numtrain + 1.0;   // GpBatch::rows_alloc
+        const double per = 3.0 * rows * (double)padded_ld(numtrain) * 8.0 + 64.0 * 1024.0 * 1024.0;
         slots = (int)std::max(1.0, std::min(64.0, 0.6 * (double)free_b / per));
     }
     h->slots = std::max(1, std::min(slots, std::max(nlocal, 1)));

