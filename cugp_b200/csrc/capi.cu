@@ -189,6 +189,11 @@ int cugp_set_tuning(const char* key, long value) {
         set_graph_max_n((int)value);
         return CUGP_OK;
     }
+    if (std::strcmp(key, "gemm_small_two") == 0) {
+        set_gemm_small_two(value != 0);
+        bump_tuning_epoch();
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "gemm_tpc") == 0) {
         if (value < 0 || value > 64) {
             set_last_error("gemm_tpc must be 0 (auto) or 1..64");

@@ -195,8 +195,8 @@ __device__ __forceinline__ TileGeom tile_geom(const GemmParams& p, int64_t t, in
 // ~cta_stride CONSECUTIVE tiles of the raster order, exactly as with one tile per CTA (giving every CTA a run of
 // consecutive tiles instead spread the in-flight set over 4x as many tile rows: 74 MB of operand panels, more than
 // the L2 holds next to the C stream -- DRAM reads of the first K = 1024 update at n = 40 000 went from 12 to 26 GB).
-template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC>
-__global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_kernel(const GemmParams p) {
+template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC, int MINB>
+__global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, MINB) dgemm_ws_kernel(const GemmParams p) {
     constexpr int NCW = WARPS_M * WARPS_N;  // consumer warps
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int MI = WM / 8, NI = WN / 8;
@@ -400,9 +400,10 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, 1) dgemm_ws_ke
 }
 
 static int g_raster_w = RASTER_W_DEFAULT;
+static int g_small_two = 1;   // 64 x 64 configuration: 1 = three stages, two CTAs per SM; 0 = four stages, one CTA per SM
 static int g_tiles_per_cta = 0;  // 0: by grid size; otherwise forced (cugp_set_tuning("gemm_tpc", v))
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC, int MINB>
 void launch_ws(const GemmParams& p_in, cudaStream_t stream) {
     constexpr int NT = (WARPS_M * WARPS_N + NPW) * 32;
     constexpr size_t smem =
@@ -410,7 +411,7 @@ void launch_ws(const GemmParams& p_in, cudaStream_t stream) {
         2 * NSTAGE * 8;
     static_assert(smem <= 227 * 1024, "stage buffers exceed shared memory");
     static bool configured = false;
-    auto kern = dgemm_ws_kernel<BM, BN, WARPS_M, WARPS_N, NSTAGE, A_KC, B_KC>;
+    auto kern = dgemm_ws_kernel<BM, BN, WARPS_M, WARPS_N, NSTAGE, A_KC, B_KC, MINB>;
     if (!configured) {
         CUGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -456,17 +457,18 @@ void launch_ws(const GemmParams& p_in, cudaStream_t stream) {
     CUGP_CUDA(cudaGetLastError());
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, int MINB = 1>
 void launch_layout(const GemmParams& p, bool a_kc, bool b_kc, cudaStream_t stream) {
-    if (a_kc && b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, true, true>(p, stream);
-    else if (a_kc && !b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, true, false>(p, stream);
-    else if (!a_kc && !b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, false, false>(p, stream);
-    else launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, false, true>(p, stream);
+    if (a_kc && b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, true, true, MINB>(p, stream);
+    else if (a_kc && !b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, true, false, MINB>(p, stream);
+    else if (!a_kc && !b_kc) launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, false, false, MINB>(p, stream);
+    else launch_ws<BM, BN, WARPS_M, WARPS_N, NSTAGE, false, true, MINB>(p, stream);
 }
 
 }  // namespace
 
 void set_gemm_tiles_per_cta(int v) { g_tiles_per_cta = v; }
+void set_gemm_small_two(int v) { g_small_two = v; }
 void set_gemm_raster_width(int v) { g_raster_w = v > 0 ? v : RASTER_W_DEFAULT; }
 
 int gemm_tile_m(GemmConfig cfg) { return cfg == GEMM_BIG ? 128 : 64; }
@@ -481,7 +483,12 @@ void launch_gemm(const GemmParams& p, bool a_kc, bool b_kc, GemmConfig cfg, cuda
     switch (cfg) {
         case GEMM_BIG: launch_layout<128, 128, 2, 4, 3>(p, a_kc, b_kc, stream); break;
         case GEMM_TALL: launch_layout<64, 128, 2, 4, 3>(p, a_kc, b_kc, stream); break;
-        default: launch_layout<64, 64, 2, 2, 4>(p, a_kc, b_kc, stream); break;
+        // 64 x 64 tiles: three stages = 111 KB, so TWO CTAs share an SM (the 4-stage, one-CTA form ran at half the DMMA
+        // rate: one math warp per scheduler cannot hide its own fragment loads)
+        default:
+            if (g_small_two) launch_layout<64, 64, 2, 2, 3, 2>(p, a_kc, b_kc, stream);
+            else launch_layout<64, 64, 2, 2, 4>(p, a_kc, b_kc, stream);
+            break;
     }
 }
 

@@ -165,7 +165,27 @@ static void potrf_trailing(double* A, int64_t ld, int64_t sA, int nrows, int J0,
 // Both step(J+2) and U2(J) touch block column J+2: step(J+2) waits for U2(J).
 static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, double* invd, int64_t sInvd, double* logdet_part,
                         int nblk, int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la,
-                        int* stepsync, double* steppub, int id_rows) {
+                        FusedCtx* fx) {
+    int* stepsync = fx->sync;
+    double* steppub = fx->pub;
+    const int id_rows = fx->id_rows;
+    fx->invd_done = false;   // the 128x128 inverses of the diagonal blocks are not a by-product here: GpBatch::ensure_invd
+    // With the identity rows, column block J of U = L^-T (rows < Jend) is final after step(J): K^-1 = U U^T is accumulated
+    // block column by block column on the main stream, in the chain's shadow, instead of one LAUUM launch after it.
+    auto kinv_update = [&](int J0, int Jend, cudaStream_t s) {
+        if (!id_rows || !fx->kinv) return;
+        GemmParams q{};
+        const double* U = A + (int64_t)(n + 1) * ld + J0;     // identity rows start below the right-hand-side row
+        q.A = U; q.lda = ld; q.sA = sA;
+        q.B = U; q.ldb = ld; q.sB = sA;
+        q.C = fx->kinv; q.ldc = ld; q.sC = sA;
+        q.M = Jend; q.N = Jend; q.K = Jend - J0;
+        q.alpha = 1.0; q.beta = 1.0;
+        q.batch = batch;
+        q.lower_tiles = 1;
+        launch_gemm(q, true, true, pick_config(Jend, Jend, batch, true), s);
+        if (launches) ++*launches;
+    };
     CUGP_CUDA(cudaMemsetAsync(stepsync, 0, (size_t)batch * nblk * 4 * sizeof(int), st));
     const bool ahead = la && la->st2 && nblk >= 3 && lookahead_enabled();
     // one launch per step only while all its CTAs are resident together (the row tiles wait on their SMs for the
@@ -198,9 +218,8 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
             const int J0 = J * kDiag, Jend = std::min(n, J0 + kDiag), Jend2 = std::min(n, Jend + kDiag);
             step(J0, J > 0, st);
             potrf_trailing(A, ld, sA, rows_at(Jend), J0, Jend, Jend2, n, batch, st, launches, prof);
+            kinv_update(J0, Jend, st);
         }
-        launch_trtri_diag(A, ld, sA, n, invd, sInvd, batch, st);
-        if (launches) ++*launches;
         return;
     }
     cudaStream_t s2 = la->st2;
@@ -218,21 +237,21 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
         const int J0 = J * kDiag, Jend = std::min(n, J0 + kDiag), Jend2 = std::min(n, Jend + kDiag);
         if (J >= 2) CUGP_CUDA(cudaStreamWaitEvent(s2, evU(J - 2), 0));
         step(J0, J > 0, s2);
-        if (Jend2 >= n) continue;   // nothing right of block J+1
+        if (Jend2 >= n && !(id_rows && fx->kinv)) continue;   // nothing right of block J+1
         CUGP_CUDA(cudaEventRecord(evP(J), s2));
         CUGP_CUDA(cudaStreamWaitEvent(st, evP(J), 0));
-        potrf_trailing(A, ld, sA, rows_at(Jend), J0, Jend, Jend2, n, batch, st, launches, prof);   // U2(J)
-        CUGP_CUDA(cudaEventRecord(evU(J), st));
+        if (Jend2 < n) {
+            potrf_trailing(A, ld, sA, rows_at(Jend), J0, Jend, Jend2, n, batch, st, launches, prof);   // U2(J)
+            CUGP_CUDA(cudaEventRecord(evU(J), st));
+        }
+        kinv_update(J0, Jend, st);
     }
-    launch_trtri_diag(A, ld, sA, n, invd, sInvd, batch, s2);   // off-diagonal 32x32 blocks of the 128x128 inverses
-    if (launches) ++*launches;
     CUGP_CUDA(cudaEventRecord(ev_end, s2));
     CUGP_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
 }
 
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part, int batch,
-                   cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la, int rhs_rows, int* stepsync,
-                   double* steppub, int id_rows) {
+                   cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la, int rhs_rows, FusedCtx* fx) {
     if (prof && !prof->on) prof = nullptr;
     const int nrows = n + rhs_rows;
     const int nblk = cdiv(n, kDiag);
@@ -240,11 +259,14 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
     const int npanels = cdiv(n, NB);
     if (la) la->panel_events = false;
     // (a batch wider than ~10 matrices is throughput bound: there the batched GEMM chain of round 1 is as fast)
-    if (stepsync && steppub && g_fused_step && NB == kDiag && batch <= g_fused_max_batch) {
-        potrf_fused(A, ld, sA, n, nrows, invd, sInvd, logdet_part, nblk, batch, st, launches, prof, la, stepsync, steppub, id_rows);
+    if (fx && fx->sync && fx->pub && g_fused_step && NB == kDiag && batch <= g_fused_max_batch) {
+        potrf_fused(A, ld, sA, n, nrows, invd, sInvd, logdet_part, nblk, batch, st, launches, prof, la, fx);
         return;
     }
-    if (id_rows) throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};   // identity rows exist on the fused path only
+    if (fx) {
+        if (fx->id_rows) throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};   // identity rows: fused path only
+        fx->invd_done = true;
+    }
     if (!la || !la->st2 || npanels < 3 || !lookahead_enabled()) {
         for (int J0 = 0; J0 < n; J0 += NB) {
             const int Jend = std::min(n, J0 + NB);
@@ -535,9 +557,12 @@ void GpBatch::build_K(int full) {
 
 void GpBatch::potrf(bool with_rhs) {
     auto body = [&] {
+        FusedCtx fx{stepsync, steppub, 0, nullptr, false};
         potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la,
-                      with_rhs ? 1 : 0, stepsync, steppub);
+                      with_rhs ? 1 : 0, &fx);
+        have_invd = fx.invd_done;
     };
+    have_invd = !fused_step_applies(n, B);     // what a replayed graph leaves behind
     if (with_rhs || !run_graphed(graph_potrf, body)) body();   // graph_potrf holds the rhs-free sequence only
 }
 
@@ -552,15 +577,31 @@ void GpBatch::potrf_with_rhs() {
         if (id) {
             launch_init_identity(Tt(), ld, mat_stride(), n, B, st);
             launches++;
+            for (int b = 0; b < B; b++)   // K^-1 is accumulated block column by block column during the factorisation
+                CUGP_CUDA(cudaMemsetAsync(Wb + (int64_t)b * mat_stride(), 0, (size_t)n * ld * sizeof(double), st));
         }
+        FusedCtx fx{stepsync, steppub, id ? n : 0, id ? Wb : nullptr, false};
         potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la,
-                      id ? 1 + n : 1, stepsync, steppub, id ? n : 0);
+                      id ? 1 + n : 1, &fx);
+        have_invd = fx.invd_done;
         const double* zrow = Kb + (int64_t)n * ld;
         launch_ll_finalize(zrow, zrow, mat_stride(), n, logdet_part, nblk, scal, B, st);
         launches += 2;
     };
+    if (id) ensure_TW();
+    have_invd = !fused_step_applies(n, B);     // what a replayed graph leaves behind
     if (!run_graphed(id ? graph_potrf_id : graph_potrf_rhs, body)) body();
     have_Tt = id;
+    have_Kinv = id;   // accumulated alongside (lower triangle of Wb)
+}
+
+// 128x128 inverses of L's diagonal blocks: a by-product of the round-1 launch chain, one extra launch after the fused
+// steps -- paid only by the paths that need them (backward sweep, TRTRI recursion).
+void GpBatch::ensure_invd() {
+    if (have_invd) return;
+    launch_trtri_diag(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, B, st);
+    launches++;
+    have_invd = true;
 }
 
 void GpBatch::prof_begin() {
@@ -665,6 +706,7 @@ void GpBatch::solve() {
         launches += 2;
     } else {
         const int64_t sI = (int64_t)nblk * kDiag * kDiag;
+        ensure_invd();
         launch_copy_rows(zrow, mat_stride(), work, n, n, B, st);  // the sweep consumes its right-hand side
         const int nev = trsv_backward_events(n);
         while ((int)bwd_ev.size() < nev) {
@@ -697,6 +739,7 @@ void GpBatch::trtri() {
     }
     join_T();
     ensure_TW();
+    ensure_invd();
     trtri_recursive(Kb, Tb, Wb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, B, st, &launches);
     have_T = true;
     have_Kinv = false;
@@ -752,22 +795,14 @@ void GpBatch::gradient_launch() {
     wants_inverse = true;
     factorize();
     if (have_Tt) {
-        // L^-T came out of the factorisation: alpha = L^-T z and K^-1 = L^-T L^-1 are two launches
-        if (!have_alpha || !have_Kinv) {
-            ensure_TW();
-            auto body = [&] {
-                have_alpha = have_Kinv = false;
-                solve();
-                lauum();
-            };
-            if (run_graphed(graph_inv_id, body)) have_alpha = have_Kinv = true;
-            solve();
-            lauum();
-        }
+        // L^-T and K^-1 = L^-T L^-1 came out of the factorisation: only alpha = L^-T z is left
+        solve();
+        lauum();
     } else {
         if (!have_T && !have_alpha && !have_Kinv) {
             // the whole inverse chain (TRTRI recursion, alpha = T^T z, LAUUM) is theta independent: one graph replay
             ensure_TW();
+            ensure_invd();
             auto body = [&] {
                 have_T = have_alpha = have_Kinv = false;
                 trtri();   // before solve(): alpha then is a single pass over T

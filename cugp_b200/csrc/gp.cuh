@@ -19,6 +19,15 @@ struct PotrfLookahead {
     bool panel_events = false;   // the last potrf_blocked call took the look-ahead path: ev[2J] = "panel J is final"
 };
 
+// What the fused block-step path of potrf_blocked needs / reports (cholstep.cu).
+struct FusedCtx {
+    int* sync;          // [batch][nblk][4]
+    double* pub;        // chol_step_pub_doubles(batch)
+    int id_rows;        // > 0: that many identity rows follow the right-hand-side rows (they leave as L^-T)
+    double* kinv;       // with id_rows: K^-1 = L^-T L^-1 is accumulated here (lower triangle, zeroed by the caller); may be null
+    bool invd_done;     // out: the 128x128 inverses of the diagonal blocks were produced (round-1 chain) or not (fused)
+};
+
 struct GpBatch {
     int B = 0, n = 0, d = 0, dp = 0, nblk = 0;  // B: GPs the launches carry (<= Bcap, see set_active)
     int Bcap = 0;                               // GPs the buffers are sized for
@@ -52,6 +61,8 @@ struct GpBatch {
     double theta[3] = {0, 0, 0};
     Hyper h{};
     bool have_data = false, have_L = false, have_alpha = false, have_T = false, have_Kinv = false;
+    bool have_invd = false;     // invd holds the inverses of L's diagonal blocks (ensure_invd)
+    void ensure_invd();
     bool have_Tt = false;       // rows n+1..2n of Kb hold L^-T (the identity rode through the factorisation)
     bool wants_inverse = false; // this batch has asked for a gradient / prediction before: factorise with the identity rows
     long launches = 0;  // kernels launched since the last reset (bench.py `gpu_launches`)
@@ -108,7 +119,7 @@ struct GpBatch {
     // an inverse still running on the third stream, then the cached state is dropped.
     void invalidate() {
         join_T();
-        have_L = have_alpha = have_T = have_Kinv = have_Tt = t_valid = false;
+        have_L = have_alpha = have_T = have_Kinv = have_Tt = have_invd = t_valid = false;
     }
 
     void build_K(int full);                 // K1 into Kb
@@ -142,7 +153,7 @@ struct GpBatch {
 // 128x128 diagonal blocks and per-block log-determinant partials as by-products.
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part,
                    int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof = nullptr, PotrfLookahead* la = nullptr,
-                   int rhs_rows = 0, int* stepsync = nullptr, double* steppub = nullptr, int id_rows = 0);
+                   int rhs_rows = 0, FusedCtx* fx = nullptr);
 // true: an n x n factorisation of `batch` matrices takes the fused block-step path (outer width 128, batch small enough)
 bool fused_step_applies(int n, int batch);
 void set_idrows_max_n(int n);   // largest n whose factorisation carries the identity rows (0: never)

@@ -6,10 +6,10 @@ NG=$(nvidia-smi -L | wc -l)
 for N in 1 2 4 8; do
   [ $N -gt $NG ] && continue
   if [ $N -eq 1 ]; then
-    timeout 300 python bench.py --workload c4 --gpus 1 --steps 6 --warmup 3 --no-cpu > gpurun_out/bench_c4_${N}gpu.log 2> gpurun_out/bench_c4_${N}gpu.err
+    timeout 300 python bench.py --workload c4 --gpus 1 --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_c4_${N}gpu.log 2> gpurun_out/bench_c4_${N}gpu.err
   else
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + N)) \
-      bench.py --workload c4 --gpus $N --steps 6 --warmup 3 --no-cpu > gpurun_out/bench_c4_${N}gpu.log 2> gpurun_out/bench_c4_${N}gpu.err
+      bench.py --workload c4 --gpus $N --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_c4_${N}gpu.log 2> gpurun_out/bench_c4_${N}gpu.err
   fi
   echo "N=$N rc=$?"; tail -1 gpurun_out/bench_c4_${N}gpu.log | python -c "
 import json,sys
