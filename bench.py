@@ -368,6 +368,62 @@ def bcm_block(cg, torch, dist, flush, m=10000):
     return out
 
 
+def library_baseline(cg, torch, sizes=(10000, 20000)):
+    """Informative same-box LIBRARY baseline: the reference's own GPU generation -- cuSOLVER potrf,
+    cuBLAS trsm / gemm, built unchanged for sm_100 (oracle/_ref/libcugp_refgpu.so) -- and a plain cuSOLVER Cholesky
+    (torch.linalg.cholesky) next to this library at the same n and theta.  Each reference size runs in its own process
+    (it keeps global device state and never frees its workspaces).  Never on the product path."""
+    from cugp_b200.loaders import synthetic_sine
+    out = []
+    for n in sizes:
+        row = {"n": n}
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "refgpu_time.py"), str(n)], capture_output=True,
+                               text=True, timeout=600)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            row["reference_gpu"] = json.loads(lines[-1]) if lines else {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:
+            row["reference_gpu"] = {"error": repr(e)}
+        try:
+            X, y = synthetic_sine(n, 10)
+            g = cg.Covsum(n, 10)
+            g.set_data(X, y)
+            ts, tg, tc = [], [], []
+            for i in range(4):
+                g.set_loghyperparam([TH_B[0] + 1e-7 * i, TH_B[1], TH_B[2]])
+                t = time.perf_counter()
+                ll = g.loglik_resident()
+                ts.append(time.perf_counter() - t)
+                t = time.perf_counter()
+                gr = g.grad_resident()
+                tg.append(time.perf_counter() - t)
+            for i in range(2):
+                g.set_loghyperparam([TH_B[0] + 1e-7 * (i + 9), TH_B[1], TH_B[2]])
+                tc.append(g.factorize_resident()[1])
+            g.set_loghyperparam(TH_B)
+            row["this_library"] = {"loglik_ms": 1e3 * min(ts[1:]), "grad_after_loglik_ms": 1e3 * min(tg[1:]),
+                                   "cholesky_ms": min(tc), "ll": g.loglik_resident(), "grad": [float(v) for v in g.grad_resident()]}
+            K = torch.from_numpy(g.compute_K_train(X)).cuda() if n <= 20000 else None
+            g.close()
+            if K is not None:
+                torch.linalg.cholesky(K)
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                torch.linalg.cholesky(K)
+                torch.cuda.synchronize()
+                row["cusolver_potrf_ms"] = 1e3 * (time.perf_counter() - t)
+                del K
+        except Exception as e:
+            row["this_library"] = {"error": repr(e)}
+        rg, tl = row.get("reference_gpu", {}), row.get("this_library", {})
+        if "loglik_ms" in rg and "loglik_ms" in tl:
+            row["speedup_loglik"] = rg["loglik_ms"] / tl["loglik_ms"]
+            row["speedup_loglik_plus_grad"] = (rg["loglik_ms"] + rg["grad_ms"]) / (tl["loglik_ms"] + tl["grad_after_loglik_ms"])
+            row["ll_rel_diff"] = abs(rg["ll"] - tl["ll"]) / abs(tl["ll"])
+        out.append(row)
+    return out
+
+
 def correctness_block(cg, L, X, y, n):
     """Outside the timed region: is the factorisation of THIS size right?  (The reference printed a Cholesky residual
     after every factorisation, cuda_src/cuda_gp.cu:1126-1139.)  residual: ||K alpha - y|| / ||y|| with K rebuilt matrix-free
@@ -638,6 +694,10 @@ def main():
                            "algorithmic_flops_per_launch": "m(m+1)*K for an m x m trailing block (lower triangle, 2 flop/MAC)"}
     if a.workload in ("c5", "c3") and not a.no_extra:
         out["correctness"] = correctness_block(cg, L, X, y, n)
+        try:
+            out["library_baseline"] = library_baseline(cg, torch)
+        except Exception as e:
+            out["library_baseline"] = {"error": repr(e)}
     out["fp64_peaks_tflops"] = dict(fp64, cublas_dgemm_8192=cublas, nominal=NOMINAL_FP64_TFLOPS)
     out["hbm"] = {"copy_probe_gbs": copy_gbs, "peak_gbs": pk.get("hbm_gbs"), "peak_source": pk_src}
     if "phases_ms" in out and pk.get("hbm_gbs"):

@@ -166,6 +166,7 @@ def build(ref: bool = True) -> None:
     subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     if ref and os.path.isdir("/root/reference"):
         subprocess.run(["make", "-C", _HERE, "-s", "ref"], check=True)
+        subprocess.run(["make", "-C", _HERE, "-s", "refgpu"], check=True)
 
 
 def port() -> CpuGP:
@@ -176,6 +177,13 @@ def port() -> CpuGP:
             build(ref=False)
         _PORT = CpuGP(path, "oracle_", "port")
     return _PORT
+
+
+def reference_gpu_path():
+    """The reference's own cuSOLVER / cuBLAS GPU variant (cuda_bettersinglenode_ver2/cuda_gp.cu, unchanged, sm_100), or
+    None when it has not been built.  bench.py's `library_baseline` leg is its only user."""
+    path = os.path.join(_HERE, "_ref", "libcugp_refgpu.so")
+    return path if os.path.exists(path) else None
 
 
 def reference():

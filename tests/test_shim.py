@@ -91,6 +91,24 @@ def test_reference_drivers_build_unchanged_against_shim():
     assert os.path.exists(os.path.join(OUT, "serial_gp")) and os.path.exists(os.path.join(OUT, "distributed_ver1"))
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources only exist in the build container")
+def test_reference_gpu_flavour_driver_builds_unchanged_against_facade():
+    """Row f4: the reference's GPU-generation driver -- cuda_bettersinglenode_ver2/main.cpp (socket master/worker main,
+    :132-224) and cg_solver.cpp (its Polack-Ribiere loop over compute_log_likelihood / compute_gradient_log_hyperparams,
+    :191-425), plus its csapp.cpp -- compiled WHERE THEY LIE, unchanged, and linked against libcugp.so through
+    include/cugp_shim/cuda_gp.h instead of the reference's cuda_gp.cu (cuSOLVER / cuBLAS)."""
+    _ensure_lib()
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(REF, "cuda_bettersinglenode_ver2")
+    exe = os.path.join(OUT, "cuda_bettersinglenode_main")
+    _gxx(["-I" + INC, "-I" + os.path.join(REF, "cuda_src"), "-include", os.path.join(ROOT, "oracle", "ref_compat.h"),
+          "-fpermissive", os.path.join(src, "main.cpp"), os.path.join(src, "cg_solver.cpp"), os.path.join(src, "csapp.cpp"),
+          os.path.join(ROOT, "tests", "shim", "cuda_gp_link.cpp"), "-o", exe, "-lpthread", *_link_flags()])
+    assert os.path.exists(exe)
+    need = {l.split()[-1] for l in subprocess.run(["nm", "-u", exe], capture_output=True, text=True).stdout.splitlines() if "cugp_" in l}
+    assert need, "the driver must reach the library through the facade"
+
+
 def _run(exe, cwd=None, timeout=600, args=()):
     env = dict(os.environ, LD_LIBRARY_PATH=LIBDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([exe, *args], capture_output=True, text=True, cwd=cwd, env=env, timeout=timeout)
@@ -162,6 +180,37 @@ def test_reference_bcm_driver_runs_on_the_shim():
     got = [float(v) for v in finals[-1]]
     th, _, _ = oracle.port().cg_solve(d["X"], d["y"], [1.5, 1.5, 1.5], K=4)
     assert [f"{v:.6f}" for v in got] == [f"{v:.6f}" for v in th], (got, th)
+
+
+@pytest.mark.gpu
+def test_reference_gpu_flavour_driver_runs_on_the_facade():
+    """The unchanged cuda_bettersinglenode_ver2 driver as master of a 1-worker run (main.cpp:189-210): setup() on the
+    128 x 2 set (it asks for 8192 rows; setup clamps to the file), theta0 = 0.5, its own cg_solve.  The optimum
+    it prints ("PLEASE-SEE  3", cg_solver.cpp:415) must be the CPU oracle's from the same start -- which is the optimum of
+    the reference's own log REF:3183 (0.882908, 0.098703, -2.971479) to five digits."""
+    exe = os.path.join(OUT, "cuda_bettersinglenode_main")
+    if not os.path.exists(exe):
+        pytest.skip("driver binary not built (needs the reference sources; built in the CPU container)")
+    from oracle import oracle
+    from tests.conftest import load_data
+    d = load_data("si128x2")
+    with tempfile.TemporaryDirectory() as t:
+        os.makedirs(os.path.join(t, "chunked_dataset"))
+        os.makedirs(os.path.join(t, "run"))
+        with open(os.path.join(t, "chunked_dataset", "siproper_9192_10_chunk0.txt"), "w") as f:
+            f.write("128 2\n")
+            for row in d["X"]:
+                f.write(" ".join(repr(float(v)) for v in row) + "\n")
+        with open(os.path.join(t, "chunked_dataset", "siproper_9192_10_label0.txt"), "w") as f:
+            for v in d["y"]:
+                f.write(repr(float(v)) + "\n")
+        out = _run(exe, cwd=os.path.join(t, "run"), args=["node0", "node0", "1"])
+    finals = re.findall(r"PLEASE-SEE\s+3:\s*(\S+), (\S+), (\S+)", out)
+    assert finals, out[-2000:]
+    got = np.array([float(v) for v in finals[-1]])
+    th, _, _ = oracle.port().cg_solve(d["X"], d["y"], [0.5, 0.5, 0.5], K=0)
+    assert np.allclose(got, th, rtol=0, atol=2e-6), (got, th)
+    assert np.allclose(got, [0.882908, 0.098703, -2.971479], rtol=0, atol=5e-6)      # REF:3183
 
 
 def _gpu_count():
