@@ -154,6 +154,14 @@ int cugp_set_tuning(const char* key, long value) {
         set_idrows_max_n((int)value);
         return CUGP_OK;
     }
+    if (std::strcmp(key, "adaptive_nb") == 0) {
+        set_adaptive_nb(value != 0);
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "fused_panel") == 0) {
+        set_fused_panel(value != 0);
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "fused_max_batch") == 0) {
         if (value < 0) return CUGP_ERR_INVALID;
         set_fused_max_batch((int)value);

@@ -98,27 +98,51 @@ bool fused_step_applies(int n, int batch) {
 // One outer panel [J0, Jend): right-looking over its 128-column blocks, full height, updates confined to the panel.
 // `nrows` >= n: rows n.. of A are appended right-hand sides (y^T): they ride through the TRSM and the updates like
 // any other row below the diagonal, which performs the forward substitution L z = y for free (z^T ends up in row n).
+static int g_fused_panel = 1;   // outer width > 128: the diagonal block + TRSM of every 128-column block as the fused step
+void set_fused_panel(int v) { g_fused_panel = v; bump_tuning_epoch(); }
+
 static void potrf_panel(double* A, int64_t ld, int64_t sA, int n, int nrows, int J0, int Jend, double* invd, int64_t sInvd,
-                        double* logdet_part, int nblk, int batch, cudaStream_t st, long* launches) {
+                        double* logdet_part, int nblk, int batch, cudaStream_t st, long* launches, FusedCtx* fx = nullptr) {
+    static const int sms = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
+    const bool fused = fx && fx->sync && fx->pub && g_fused_step && g_fused_panel && batch <= g_fused_max_batch;
     for (int j0 = J0; j0 < Jend; j0 += kDiag) {
         const int blk = j0 / kDiag;
-        launch_potrf_diag(A, ld, sA, n, j0, invd, sInvd, logdet_part, nblk, blk, batch, st);
-        if (launches) ++*launches;
         const int nbk = std::min(kDiag, n - j0);  // < 128 only for the last block
         const int r0 = j0 + nbk;
         const int m = nrows - r0;
-        if (m <= 0) break;
         double* A21 = A + (int64_t)r0 * ld + j0;
-        // TRSM panel: L21 = A21 * inv(L11)^T, in place (each CTA owns whole rows of the panel).
-        GemmParams p{};
-        p.A = A21; p.lda = ld; p.sA = sA;
-        p.B = invd + (int64_t)blk * kDiag * kDiag; p.ldb = kDiag; p.sB = sInvd;
-        p.C = A21; p.ldc = ld; p.sC = sA;
-        p.M = m; p.N = nbk; p.K = nbk;
-        p.alpha = 1.0; p.beta = 0.0;
-        p.batch = batch;
-        launch_gemm(p, true, true, GEMM_TALL, st);
-        if (launches) ++*launches;
+        if (fused) {
+            // diagonal block (slab factorisation, 32x32 inverses) and the TRSM of every row below in the fused step kernel
+            // (cholstep.cu) without its prologue: one launch while its CTAs fit the chip together, else two
+            const bool split = (int64_t)batch * chol_step_ctas(n, nrows, j0) > sms;
+            if (!split) {
+                launch_chol_step(A, ld, sA, n, nrows, j0, fx->pub, logdet_part, nblk, fx->sync, 0, batch, st, 0);
+                if (launches) ++*launches;
+            } else {
+                launch_chol_step(A, ld, sA, n, nrows, j0, fx->pub, logdet_part, nblk, fx->sync, 0, batch, st, 1);
+                launch_chol_step(A, ld, sA, n, nrows, j0, fx->pub, logdet_part, nblk, fx->sync, 0, batch, st, 2);
+                if (launches) *launches += 2;
+            }
+            if (m <= 0) break;
+        } else {
+            launch_potrf_diag(A, ld, sA, n, j0, invd, sInvd, logdet_part, nblk, blk, batch, st);
+            if (launches) ++*launches;
+            if (m <= 0) break;
+            // TRSM panel: L21 = A21 * inv(L11)^T, in place (each CTA owns whole rows of the panel).
+            GemmParams p{};
+            p.A = A21; p.lda = ld; p.sA = sA;
+            p.B = invd + (int64_t)blk * kDiag * kDiag; p.ldb = kDiag; p.sB = sInvd;
+            p.C = A21; p.ldc = ld; p.sC = sA;
+            p.M = m; p.N = nbk; p.K = nbk;
+            p.alpha = 1.0; p.beta = 0.0;
+            p.batch = batch;
+            launch_gemm(p, true, true, GEMM_TALL, st);
+            if (launches) ++*launches;
+        }
         // remaining columns of the panel: A[r0:, r0:Jend] -= L21 L21[0:w]^T, lower trapezoid
         const int w = Jend - r0;
         if (w <= 0) continue;
@@ -163,9 +187,11 @@ static void potrf_trailing(double* A, int64_t ld, int64_t sA, int nrows, int J0,
 // column J-1 to block column J (its prologue), so the trailing update of panel J only covers the columns right of
 // block J+1 -- U2(J) -- and, with look-ahead, runs on the main stream while the panel stream is already at step(J+1).
 // Both step(J+2) and U2(J) touch block column J+2: step(J+2) waits for U2(J).
+// `nblk_stride`: blocks per matrix of logdet_part / sync (the caller may pass both advanced to the first block of a
+// trailing sub-matrix); `nblk`: block columns of THIS n x n factorisation.
 static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, double* invd, int64_t sInvd, double* logdet_part,
-                        int nblk, int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la,
-                        FusedCtx* fx) {
+                        int nblk_stride, int nblk, int batch, cudaStream_t st, long* launches, GpBatch::Prof* prof,
+                        PotrfLookahead* la, FusedCtx* fx) {
     int* stepsync = fx->sync;
     double* steppub = fx->pub;
     const int id_rows = fx->id_rows;
@@ -186,7 +212,8 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
         launch_gemm(q, true, true, pick_config(Jend, Jend, batch, true), s);
         if (launches) ++*launches;
     };
-    CUGP_CUDA(cudaMemsetAsync(stepsync, 0, (size_t)batch * nblk * 4 * sizeof(int), st));
+    if (nblk == nblk_stride)   // (a trailing sub-matrix: the caller has zeroed the whole array)
+        CUGP_CUDA(cudaMemsetAsync(stepsync, 0, (size_t)batch * nblk * 4 * sizeof(int), st));
     const bool ahead = la && la->st2 && nblk >= 3 && lookahead_enabled();
     // one launch per step only while all its CTAs are resident together (the row tiles wait on their SMs for the
     // diagonal CTA); a wider batch takes the diagonal part and the row tiles as two launches
@@ -205,11 +232,11 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
     auto step = [&](int J0, int prologue, cudaStream_t s) {
         const int nr = rows_at(std::min(n, J0 + kDiag));
         if (!split) {
-            launch_chol_step(A, ld, sA, n, nr, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 0);
+            launch_chol_step(A, ld, sA, n, nr, J0, steppub, logdet_part, nblk_stride, stepsync, prologue, batch, s, 0);
             if (launches) ++*launches;
         } else {
-            launch_chol_step(A, ld, sA, n, nr, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 1);
-            launch_chol_step(A, ld, sA, n, nr, J0, steppub, logdet_part, nblk, stepsync, prologue, batch, s, 2);
+            launch_chol_step(A, ld, sA, n, nr, J0, steppub, logdet_part, nblk_stride, stepsync, prologue, batch, s, 1);
+            launch_chol_step(A, ld, sA, n, nr, J0, steppub, logdet_part, nblk_stride, stepsync, prologue, batch, s, 2);
             if (launches) *launches += 2;
         }
     };
@@ -250,30 +277,61 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
     CUGP_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
 }
 
+static int g_adaptive_nb = 0;   // (measured slower, profiles/r2_adaptive_nb.txt: the last wide panel loses its overlap) 1: the outer width follows the REMAINING size; its last part takes the fused 128 path
+void set_adaptive_nb(int v) { g_adaptive_nb = v; bump_tuning_epoch(); }
+static bool nb_is_forced() { return g_potrf_nb != 0 || std::getenv("CUGP_POTRF_NB") != nullptr; }
+
 void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64_t sInvd, double* logdet_part, int batch,
                    cudaStream_t st, long* launches, GpBatch::Prof* prof, PotrfLookahead* la, int rhs_rows, FusedCtx* fx) {
     if (prof && !prof->on) prof = nullptr;
     const int nrows = n + rhs_rows;
     const int nblk = cdiv(n, kDiag);
     const int NB = potrf_outer_width(n);
-    const int npanels = cdiv(n, NB);
     if (la) la->panel_events = false;
     // (a batch wider than ~10 matrices is throughput bound: there the batched GEMM chain of round 1 is as fast)
-    if (fx && fx->sync && fx->pub && g_fused_step && NB == kDiag && batch <= g_fused_max_batch) {
-        potrf_fused(A, ld, sA, n, nrows, invd, sInvd, logdet_part, nblk, batch, st, launches, prof, la, fx);
+    const bool fused_ok = fx && fx->sync && fx->pub && g_fused_step && batch <= g_fused_max_batch;
+    if (fused_ok && NB == kDiag) {
+        potrf_fused(A, ld, sA, n, nrows, invd, sInvd, logdet_part, nblk, nblk, batch, st, launches, prof, la, fx);
         return;
     }
+    const bool fpanel = fused_ok && g_fused_panel;
     if (fx) {
-        if (fx->id_rows) throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};   // identity rows: fused path only
-        fx->invd_done = true;
+        if (fx->id_rows) throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};   // identity rows: outer width 128 only
+        fx->invd_done = !fpanel;
     }
+    if (fpanel) CUGP_CUDA(cudaMemsetAsync(fx->sync, 0, (size_t)batch * nblk * 4 * sizeof(int), st));
+    // Panel boundaries.  With the fused step available the outer width follows the size that is LEFT (a wide panel only
+    // pays while its trailing update dominates the chain of block steps), and once that calls for 128 the rest -- a
+    // Cholesky of the fully updated Schur complement -- takes the fused 128-column path with its own look-ahead.
+    std::vector<int> P;
+    int tail = n;
+    const bool adaptive = fpanel && g_adaptive_nb && !nb_is_forced();
+    for (int s0 = 0; s0 < n;) {
+        const int w = adaptive ? potrf_outer_width(n - s0) : NB;
+        if (adaptive && w == kDiag) {
+            tail = s0;
+            break;
+        }
+        P.push_back(s0);
+        s0 += w;
+    }
+    const int npanels = (int)P.size();
+    auto pend = [&](int J) { return J + 1 < npanels ? P[J + 1] : tail; };   // right edge of panel J (tail == n without a tail)
+    auto run_tail = [&] {
+        if (tail >= n) return;
+        FusedCtx sub = *fx;
+        sub.sync = fx->sync + (int64_t)(tail / kDiag) * 4;
+        potrf_fused(A + (int64_t)tail * (ld + 1), ld, sA, n - tail, nrows - tail, invd, sInvd, logdet_part + tail / kDiag, nblk,
+                    cdiv(n - tail, kDiag), batch, st, launches, prof, la, &sub);
+    };
     if (!la || !la->st2 || npanels < 3 || !lookahead_enabled()) {
-        for (int J0 = 0; J0 < n; J0 += NB) {
-            const int Jend = std::min(n, J0 + NB);
-            potrf_panel(A, ld, sA, n, nrows, J0, Jend, invd, sInvd, logdet_part, nblk, batch, st, launches);
+        for (int J = 0; J < npanels; J++) {
+            const int J0 = P[J], Jend = std::min(n, pend(J));
+            potrf_panel(A, ld, sA, n, nrows, J0, Jend, invd, sInvd, logdet_part, nblk, batch, st, launches, fx);
             // trailing update: A[Jend:, Jend:] -= P P^T with P = L[Jend:, J0:Jend], lower tiles, K = outer width
             potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend, n, batch, st, launches, prof);
         }
+        run_tail();
         return;
     }
     // Look-ahead of one panel: the panel stream (high priority) factors panel J+1 while the main stream applies the
@@ -292,19 +350,23 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
     CUGP_CUDA(cudaEventRecord(ev_start, st));          // K is complete on the main stream
     CUGP_CUDA(cudaStreamWaitEvent(s2, ev_start, 0));
     for (int J = 0; J < npanels; J++) {
-        const int J0 = J * NB, Jend = std::min(n, J0 + NB), Jend2 = std::min(n, Jend + NB);
-        potrf_panel(A, ld, sA, n, nrows, J0, Jend, invd, sInvd, logdet_part, nblk, batch, s2, launches);
+        const int J0 = P[J], Jend = std::min(n, pend(J));
+        // the last two-level panel before a fused tail updates ALL remaining columns on the panel stream
+        const int Jend2 = J + 1 < npanels ? std::min(n, pend(J + 1)) : n;
+        potrf_panel(A, ld, sA, n, nrows, J0, Jend, invd, sInvd, logdet_part, nblk, batch, s2, launches, fx);
         CUGP_CUDA(cudaEventRecord(evP(J), s2));
         if (Jend >= n) break;
         if (J >= 1) CUGP_CUDA(cudaStreamWaitEvent(s2, evU(J - 1), 0));
         potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend, Jend2, batch, s2, launches, nullptr);   // U1(J)
+        if (Jend2 >= n) continue;
         CUGP_CUDA(cudaStreamWaitEvent(st, evP(J), 0));
         potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend2, n, batch, st, launches, prof);          // U2(J)
         CUGP_CUDA(cudaEventRecord(evU(J), st));
     }
     CUGP_CUDA(cudaEventRecord(ev_end, s2));
     CUGP_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
-    la->panel_events = true;
+    la->panel_events = tail >= n;
+    run_tail();
 }
 
 void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t sM, int n, const double* invd,
@@ -562,7 +624,7 @@ void GpBatch::potrf(bool with_rhs) {
                       with_rhs ? 1 : 0, &fx);
         have_invd = fx.invd_done;
     };
-    have_invd = !fused_step_applies(n, B);     // what a replayed graph leaves behind
+    have_invd = !g_fused_step || B > g_fused_max_batch;     // what a replayed graph leaves behind
     if (with_rhs || !run_graphed(graph_potrf, body)) body();   // graph_potrf holds the rhs-free sequence only
 }
 
@@ -589,7 +651,7 @@ void GpBatch::potrf_with_rhs() {
         launches += 2;
     };
     if (id) ensure_TW();
-    have_invd = !fused_step_applies(n, B);     // what a replayed graph leaves behind
+    have_invd = !g_fused_step || B > g_fused_max_batch;     // what a replayed graph leaves behind
     if (!run_graphed(id ? graph_potrf_id : graph_potrf_rhs, body)) body();
     have_Tt = id;
     have_Kinv = id;   // accumulated alongside (lower triangle of Wb)
@@ -689,7 +751,7 @@ void GpBatch::factorize() {
     potrf_with_rhs();
     have_L = true;
     // a batch that has computed gradients / predictions before (T exists) will want T = L^-1 again: start it now
-    if (Tb && Wb && la.panel_events && !have_Tt && n <= g_overlap_max_n) enqueue_trtri_overlapped();
+    if (Tb && Wb && la.panel_events && have_invd && !have_Tt && n <= g_overlap_max_n) enqueue_trtri_overlapped();
 }
 
 // alpha = L^-T z.  With T = L^-1 at hand (gradient / prediction paths) it is one streaming pass alpha = T^T z;

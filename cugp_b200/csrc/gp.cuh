@@ -160,6 +160,8 @@ void set_idrows_max_n(int n);   // largest n whose factorisation carries the ide
 int idrows_max_n();
 void set_pred_chunk(int v); // > 0: cap on the test points one prediction chunk carries (0: by memory)
 void set_fused_max_batch(int v);   // widest batch the fused step is used for
+void set_adaptive_nb(int v);  // 1 (default 0: measured slower): outer width by the remaining size, fused 128 path for the last part
+void set_fused_panel(int v);  // 1 (default): wider outer panels also factor their 128-column blocks with the fused step
 void set_fused_step(int v); // 1 (default): one fused launch per 128-column block step when the outer width is 128
 // Tuning epoch: bumped by every tuning change so cached graphs are re-captured.  graph_max_n: largest n whose launch
 // chains are replayed as CUDA graphs (0 disables).
