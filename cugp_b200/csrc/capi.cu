@@ -154,6 +154,10 @@ int cugp_set_tuning(const char* key, long value) {
         set_idrows_max_n((int)value);
         return CUGP_OK;
     }
+    if (std::strcmp(key, "cov_fast") == 0) {   // takes effect at the next set_loghyper (the flag travels with theta)
+        set_cov_fast(value != 0);
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "adaptive_nb") == 0) {
         set_adaptive_nb(value != 0);
         return CUGP_OK;

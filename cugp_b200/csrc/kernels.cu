@@ -104,9 +104,11 @@ __device__ __forceinline__ void stage_x_tiles(double* smem, const double* Xi, in
     __syncthreads();
 }
 
-// Squared distances of the 4x4 micro-tile, accumulated in dimension order with separately rounded
-// subtract / multiply / add -- the reference's subtract_vec + dotproduct_vec (matrixops.cpp:216-229)
-// compiled without FMA contraction -- so d2 is bit-identical to the CPU path.
+// Squared distances of the 4x4 micro-tile, accumulated in dimension order.  FAST = false: separately rounded
+// subtract / multiply / add -- the reference's subtract_vec + dotproduct_vec (matrixops.cpp:216-229) compiled without FMA
+// contraction -- so d2 is bit-identical to the CPU path.  FAST = true: the multiply-add is fused (20 instead of 30 FP64
+// instructions per pair at d = 10).
+template <bool FAST>
 __device__ __forceinline__ void micro_d2(const double* xt_i, const double* xt_j, int dp, int ty, int tx,
                                          double d2[4][4]) {
 #pragma unroll
@@ -125,17 +127,19 @@ __device__ __forceinline__ void micro_d2(const double* xt_i, const double* xt_j,
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 double t = __dsub_rn(xi[a], xj[c]);
-                d2[a][c] = __dadd_rn(d2[a][c], __dmul_rn(t, t));
+                d2[a][c] = FAST ? fma(t, t, d2[a][c]) : __dadd_rn(d2[a][c], __dmul_rn(t, t));
             }
     }
 }
 
-// sf2 * exp(-d2 * 0.5 / ell_sq): same operation order as covkernel.cpp:89 (division kept as a division).
+// sf2 * exp(-d2 * 0.5 / ell_sq).  FAST = false: same operation order as covkernel.cpp:89 (division kept as a division);
+// FAST = true: one multiply by the precomputed -0.5 / ell_sq.
+template <bool FAST>
 __device__ __forceinline__ double se_kernel(double d2, const Hyper& h) {
-    return h.sf2 * exp(__ddiv_rn(__dmul_rn(-d2, 0.5), h.ell_sq));
+    return h.sf2 * exp(FAST ? d2 * h.neg_half_inv_ell_sq : __ddiv_rn(__dmul_rn(-d2, 0.5), h.ell_sq));
 }
 
-template <int MODE>
+template <int MODE, bool FAST>
 __global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs p) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) unsigned long long bar;
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs p) 
     stage_x_tiles(smem, Xi, i0, p.ni, Xj, j0, p.nj, p.dp, &bar, xt_i, xt_j);
 
     double d2[4][4];
-    micro_d2(xt_i, xt_j, p.dp, ty, tx, d2);
+    micro_d2<FAST>(xt_i, xt_j, p.dp, ty, tx, d2);
 
     if (MODE == COV_LOWER || MODE == COV_FULL) {
         double* K = p.out + b * p.sOut;
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs p) 
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 int gj = j0 + tx * 2 + 32 * (c >> 1) + (c & 1);
-                double val = se_kernel(d2[a][c], p.h);
+                double val = se_kernel<FAST>(d2[a][c], p.h);
                 if (gi == gj) val += p.h.sn2;  // covkernel.cpp:93-94
                 v[a][c] = val;
             }
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs p) 
             double v[4], s = 0.0;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                v[c] = se_kernel(d2[a][c], p.h);
+                v[c] = se_kernel<FAST>(d2[a][c], p.h);
                 s += v[c] * al[c];
             }
             if (gi < p.ni) {
@@ -253,8 +257,8 @@ __global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs p) 
                     s2 += w * p.h.sf2;  // K_ii - sn2 = sf2 * exp(0)
                     s3 += w;
                 } else {
-                    double kv = se_kernel(d2[a][c], p.h);
-                    s1 += 2.0 * (w * (kv * (d2[a][c] / p.h.ell_sq)));  // covkernel.cpp:148,186,247
+                    double kv = se_kernel<FAST>(d2[a][c], p.h);
+                    s1 += 2.0 * (w * (kv * (FAST ? d2[a][c] * p.h.inv_ell_sq : d2[a][c] / p.h.ell_sq)));  // covkernel.cpp:148,186,247
                     s2 += 2.0 * (w * kv);
                 }
             }
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(COV_THREADS) cov_matvec_kernel(const double* _
         if (tid < CT) vj[tid] = (j0 + tid < n) ? v[j0 + tid] : 0.0;
         __syncthreads();
         double d2[4][4];
-        micro_d2(xt_i, xt_j, dp, ty, tx, d2);
+        micro_d2<false>(xt_i, xt_j, dp, ty, tx, d2);   // the CHECK keeps the reference's arithmetic
 #pragma unroll
         for (int a = 0; a < 4; a++) {
             const int gi = i0 + ty * 4 + a;
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(COV_THREADS) cov_matvec_kernel(const double* _
             for (int c = 0; c < 4; c++) {
                 const int cj = tx * 2 + 32 * (c >> 1) + (c & 1), gj = j0 + cj;
                 if (gj < n) {
-                    double kv = se_kernel(d2[a][c], h);
+                    double kv = se_kernel<false>(d2[a][c], h);
                     if (gi == gj) kv += h.sn2;
                     acc[a] += kv * vj[cj];
                 }
@@ -358,17 +362,22 @@ __global__ void __launch_bounds__(COV_THREADS) cov_matvec_kernel(const double* _
     }
 }
 
-template <int MODE>
-void launch_cov(const CovArgs& a, int64_t tiles, int batch, cudaStream_t st) {
+template <int MODE, bool FAST>
+void launch_cov_impl(const CovArgs& a, int64_t tiles, int batch, cudaStream_t st) {
     size_t smem = (size_t)4 * CT * a.dp * sizeof(double);
     static size_t configured = 0;
     if (smem > configured) {
-        CUGP_CUDA(cudaFuncSetAttribute(cov_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUGP_CUDA(cudaFuncSetAttribute(cov_tile_kernel<MODE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     if (tiles <= 0 || batch <= 0) return;
-    cov_tile_kernel<MODE><<<dim3((unsigned)tiles, (unsigned)batch), COV_THREADS, smem, st>>>(a);
+    cov_tile_kernel<MODE, FAST><<<dim3((unsigned)tiles, (unsigned)batch), COV_THREADS, smem, st>>>(a);
     CUGP_CUDA(cudaGetLastError());
+}
+template <int MODE>
+void launch_cov(const CovArgs& a, int64_t tiles, int batch, cudaStream_t st) {
+    if (a.h.fast) launch_cov_impl<MODE, true>(a, tiles, batch, st);
+    else launch_cov_impl<MODE, false>(a, tiles, batch, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1074,6 +1083,10 @@ __global__ void poe_finalize_kernel(const double* PQ, int m, double* mean, doubl
 }
 
 }  // namespace
+
+static int g_cov_fast = 1;
+int cov_fast_default() { return g_cov_fast; }
+void set_cov_fast(int v) { g_cov_fast = v; }
 
 // ------------------------------------------------------------------------------------------------
 // launchers

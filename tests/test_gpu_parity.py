@@ -282,21 +282,55 @@ def test_non_pd_is_nan_not_an_error():
 
 
 # ---------------------------------------------------------------------------------------------- covariance
+@pytest.mark.parametrize("fast", [0, 1])
 @pytest.mark.parametrize("n,d", [(1, 1), (63, 3), (64, 10), (65, 7), (300, 10), (1024, 10)])
-def test_K_train_and_k_test(n, d):
+def test_K_train_and_k_test(n, d, fast):
+    """fast = 0: the reference's operation order (separately rounded sub / mul / add, a true division): the exponent is
+    bit-identical and only exp() differs from glibc's by a couple of ulp.  fast = 1 (the default): FMA accumulation and a
+    multiply by -0.5/ell^2 -- the exponent moves by a few ulp (ten fused steps), i.e. K by a few |arg| ulp, arg = |xi-xj|^2 / (2 ell^2)."""
     rng = np.random.default_rng(n + d)
     X = rng.uniform(-20, 20, (n, d)) if d == 10 else rng.uniform(-3, 3, (n, d))
-    for th in ([0.5, 0.5, 0.5], TH_B):
-        c = cg.Covsum(n, d)
-        c.set_loghyperparam(th)
-        K, Ko = c.compute_K_train(X), PORT.K_train(X, th)
-        assert np.array_equal(K, K.T)
-        assert np.array_equal(np.diag(K), np.diag(Ko))                 # sf2*exp(0)+sn2, exact
-        # off-diagonal: same argument bit for bit, exp() within a couple of ulp (subnormals: absolute)
-        assert np.all(np.abs(K - Ko) <= 8 * np.spacing(np.abs(Ko)) + 1e-320), np.abs(K - Ko).max()
-        xt = rng.uniform(-3, 3, d)
-        k, ko = c.compute_k_test(X, xt), PORT.k_test(X, th, xt)
-        assert np.all(np.abs(k - ko) <= 8 * np.spacing(np.abs(ko)) + 1e-320)
+    try:
+        assert lib().cugp_set_tuning(b"cov_fast", fast) == 0
+        for th in ([0.5, 0.5, 0.5], TH_B):
+            c = cg.Covsum(n, d)
+            c.set_loghyperparam(th)
+            K, Ko = c.compute_K_train(X), PORT.K_train(X, th)
+            assert np.array_equal(K, K.T)
+            assert np.array_equal(np.diag(K), np.diag(Ko))                 # sf2*exp(0)+sn2, exact
+            sf2 = np.exp(2 * th[1])
+            with np.errstate(divide="ignore"):
+                arg = np.where(Ko > 0, -np.log(np.maximum(Ko, 1e-320) / sf2), 745.0)
+            np.fill_diagonal(arg, 0.0)
+            ulps = 8 + (8 * np.abs(arg) if fast else 0)   # <= ~6 ulp on the exponent: 10 fused steps + the scaling
+            # off-diagonal: exp() within a couple of ulp of glibc's (subnormals: absolute)
+            assert np.all(np.abs(K - Ko) <= ulps * np.spacing(np.abs(Ko)) + 1e-320), (np.abs(K - Ko) / np.spacing(np.abs(Ko) + 1e-300)).max()
+            xt = rng.uniform(-3, 3, d)
+            k, ko = c.compute_k_test(X, xt), PORT.k_test(X, th, xt)
+            with np.errstate(divide="ignore"):
+                argk = np.where(ko > 0, -np.log(np.maximum(ko, 1e-320) / sf2), 745.0)
+            assert np.all(np.abs(k - ko) <= (8 + (8 * argk if fast else 0)) * np.spacing(np.abs(ko)) + 1e-320)
+            c.close()
+    finally:
+        lib().cugp_set_tuning(b"cov_fast", 1)
+
+
+def test_goldens_hold_with_the_reference_arithmetic_too():
+    """The strict covariance arithmetic (cov_fast = 0) is still there and still meets the goldens (C1 at both thetas)."""
+    try:
+        lib().cugp_set_tuning(b"cov_fast", 0)
+        for name in ("C1_sine1024_thA_pred8", "C1_sine1024_thB_pred16"):
+            c = GOLD[name]
+            X, y, Xt, yt = case_inputs(c)
+            g = cg.Covsum(c["n"], c["d"])
+            g.set_loghyperparam(c["theta"])
+            assert_ll(g.compute_loglikelihood(X, y), c["ll"])
+            assert_grad(g.compute_gradient_loghyperparam(X, y), c["grad"])
+            mu, var = g.compute_test_means_and_variances(X, y, Xt)
+            assert_pred(mu, var, c["mean"], c["var"], yscale=np.abs(y).max())
+            g.close()
+    finally:
+        lib().cugp_set_tuning(b"cov_fast", 1)
 
 
 # ---------------------------------------------------------------------------------------------- golden cases
