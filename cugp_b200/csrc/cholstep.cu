@@ -1,25 +1,33 @@
 // cholstep.cu -- one 128-column block step of the right-looking Cholesky as ONE launch (round 2).
 //
-// Replaces, for the latency-bound regime (outer width 128: every factorisation below n ~ 5000 and every BCM expert), the
-// chain  diag kernel -> TRSM GEMM -> next-block update GEMM  (three dependent launches, ~70 us per 128 columns) of
-// get_cholesky (common/matrixops.cpp:68-108).  The CTAs of the launch take ROLES in the order they start (an atomic
-// ticket per matrix, so a CTA only ever waits for CTAs that are already running):
+// Replaces, wherever a factorisation is bound by its chain of block steps (outer width 128: everything below n ~ 5000 and
+// every BCM expert; with `prologue` = 0 also the 128-column blocks inside wider outer panels), the chain
+//     diag kernel (40 us) -> TRSM GEMM -> next-block update GEMM        (three dependent launches, ~70 us per 128 columns)
+// of get_cholesky (common/matrixops.cpp:68-108).  The CTAs of the launch take ROLES in the order they start (an atomic
+// ticket per matrix, so a CTA only ever waits for CTAs that are already running -- no co-residency assumption beyond
+// "a started CTA makes progress"):
 //
 //   SYRKD (10 CTAs, only with `prologue`): the 32x32 lower blocks of this step's 128x128 diagonal block receive the
-//          previous block column's contribution  A_jj -= L[j, j-1] L[j, j-1]^T  (K = 128), then signal a counter.
-//   DIAG  (1 CTA): waits for that counter, factors the 128x128 block in shared memory -- four 32-column panels; one warp
-//          factors the 32x32 diagonal sub-block AND inverts it in the same register-resident column loop (row i of L and
-//          column i of inv(L) share one 32-entry array), the other 15 warps apply the previous panel's TRSM / SYRK
-//          remainder on DMMA meanwhile (look-ahead inside the CTA) -- writes L11 and the four 32x32 diagonal inverses,
-//          then releases a flag.
-//   ROWS  (one CTA per 32 rows below the block, the appended y^T row included): while DIAG works they apply the
-//          previous block column's contribution to their 32x128 tile in shared memory (the `prologue`, K = 128 on DMMA;
-//          the tile never returns to HBM in between), then wait for the flag and run the TRSM as a 4-step blocked
-//          substitution with the 32x32 inverses:  X_c = (C_c - sum_{k<c} X_k L_ck^T) inv(L_cc)^T.
+//          previous block column's contribution  A_jj -= L[j, j-1] L[j, j-1]^T  (K = 128, DMMA), then bump a counter.
+//   DIAG  (1 CTA, 16 warps): waits for that counter, loads the block, and factors it slab by slab (4 slabs of 32 columns):
+//            pivot warp      8-column panels in registers (SHFL broadcasts, branch-free rsqrt), rank-8 DMMA updates
+//            follower warps  the rows below the 32x32 sub-block follow panel by panel (named barriers: the pivot warp
+//                            only ever ARRIVES), so the in-block TRSM needs no inverse and no extra phase
+//            all warps       the slab's SYRK on the next slab's columns (critical), 12 helper warps the rest of it, the
+//                            32x32 inverse T_cc of the finished sub-block and the PUBLICATION of the finished column slab
+//                            (L(:, slab) into the matrix, L and T_cc into a 128x132 image in global memory) with a
+//                            release flag -- all in the shadow of the next slab's pivot chain
+//   ROWS  (one CTA per 32 rows below the block; appended right-hand-side / identity rows included): while DIAG works
+//          they apply the previous block column's contribution to their 32x128 tile in shared memory (the `prologue`,
+//          K = 128 on DMMA; the tile never returns to HBM in between), then follow DIAG slab by slab (acquire flag c,
+//          fetch slab c, X_c = C_c T_cc^T, C_c' -= X_c L(c', c)^T for c' > c): when DIAG finishes its last slab only one
+//          32x32x32 product is left.
 //
-// The pivot chain of the 32x32 factorisation is kept free of the shared-memory broadcast round trip (round 1's kernel
-// fed the SHFL of the next pivot from a register that also waited on the LDS of the column broadcast: 238 clocks per
-// column, see profiles/r2_diag_chain.txt).
+// Measured (profiles/r2_step_phases_*.txt, n = 1500, one B200): 70 us -> 35 us per block step; what is left is the pivot
+// chain (4 x 3.7 us), the SYRKD hand-over (3.6 us), the tile loads and the launch gap.
+// The pivot chain itself: tools/chol32_microbench.cu (profiles/r2_chol32_microbench.txt) -- a whole 32x32 factorisation
+// unrolled in one warp is bound by instruction issue and by how ptxas orders the 31-j column updates around the rsqrt
+// (240-390 clocks per column); the 8-column panel form keeps <= 7 updates per column next to the chain.
 #include "cholstep.cuh"
 
 #include <algorithm>

@@ -424,6 +424,106 @@ void trtri_recursive(const double* L, double* T, double* W, int64_t ld, int64_t 
     }
 }
 
+// In-place variants for sizes where three n x n buffers do not fit (n = 100 000: 80 GB each).
+// TRTRI: the same recursive doubling, but T overwrites L block by block (T21 = -T22 (L21 T11) only needs L21 until the
+// product tmp = L21 T11 exists) and tmp lives in a COMPACT scratch: level h needs n h / 2 doubles at most, n^2 / 4 at the
+// top level.  Single matrix.
+size_t trtri_inplace_scratch(int n) {
+    size_t need = 0;
+    for (int64_t h = kDiag; h < n; h *= 2) {
+        const int64_t full = n / (2 * h);
+        const int64_t r2 = full * 2 * h + h;
+        const int64_t rem = r2 < n ? (n - r2) : 0;
+        need = std::max<size_t>(need, (size_t)(full * h * h + rem * h));
+    }
+    return need;
+}
+void trtri_inplace(double* A, int64_t ld, int n, const double* invd, double* Wc, cudaStream_t st, long* launches) {
+    launch_scatter_invdiag(invd, 0, A, ld, 0, n, 1, st);   // diagonal blocks: L_jj -> inv(L_jj) (lower; upper never read)
+    if (launches) ++*launches;
+    for (int64_t h = kDiag; h < n; h *= 2) {
+        const int full = (int)(n / (2 * h));
+        const int64_t pair_stride = 2 * h * (ld + 1);
+        for (int pass = 0; pass < 2; pass++) {
+            int npairs, n2;
+            int64_t base;
+            double* W;
+            if (pass == 0) {
+                npairs = full; n2 = (int)h; base = 0; W = Wc;
+            } else {
+                const int64_t r2 = (int64_t)full * 2 * h + h;
+                if (r2 >= n) break;
+                npairs = 1; n2 = (int)(n - r2); base = (int64_t)full * pair_stride; W = Wc + (int64_t)full * h * h;
+            }
+            if (npairs == 0) continue;
+            const int64_t o21 = base + h * ld, o11 = base, o22 = base + h * (ld + 1);
+            GemmParams p{};  // tmp = L21 * T11   (T11 lower: k >= column tile start)
+            p.A = A + o21; p.lda = ld;
+            p.B = A + o11; p.ldb = ld;
+            p.C = W; p.ldc = h;
+            p.M = n2; p.N = (int)h; p.K = (int)h;
+            p.alpha = 1.0; p.beta = 0.0;
+            p.batch = npairs;
+            p.sA = p.sB = pair_stride;
+            p.sC = h * h;
+            p.klo_tj = 1;
+            const GemmConfig cfg = pick_config(n2, (int)h, npairs, false);
+            launch_gemm(p, true, false, cfg, st);
+            GemmParams q{};  // T21 = -T22 * tmp   (T22 lower: k < row tile end), written over L21
+            q.A = A + o22; q.lda = ld;
+            q.B = W; q.ldb = h;
+            q.C = A + o21; q.ldc = ld;
+            q.M = n2; q.N = (int)h; q.K = n2;
+            q.alpha = -1.0; q.beta = 0.0;
+            q.batch = npairs;
+            q.sA = q.sC = pair_stride;
+            q.sB = h * h;
+            q.khi_ti = 1;
+            launch_gemm(q, true, false, cfg, st);
+            if (launches) *launches += 2;
+        }
+    }
+}
+
+// LAUUM in place: K^-1 = T^T T (lower) over T, row block by row block from the top.  Row block R = [i0, i0 + ib) of the
+// result needs rows >= i0 of T only: the block's own rows are copied to a scratch of ib x ld first (with the strict
+// upper part of its diagonal block zeroed: it is the k range's only guard there), rows below are still T.
+//   C[R, 0:i0+ib] = S[:, R]^T S[:, 0:i0+ib]  +  T[i0+ib:, R]^T T[i0+ib:, 0:i0+ib]
+__global__ void zero_upper_kernel(double* S, int64_t ld, int c0, int ib) {
+    const int r = blockIdx.x, c = threadIdx.x + blockIdx.y * blockDim.x;
+    if (r < ib && c < ib && c > r) S[(int64_t)r * ld + c0 + c] = 0.0;
+}
+void lauum_inplace(double* A, int64_t ld, int n, double* S, int ib, cudaStream_t st, long* launches) {
+    for (int i0 = 0; i0 < n; i0 += ib) {
+        const int rows = std::min(ib, n - i0), cols = i0 + rows;
+        CUGP_CUDA(cudaMemcpy2DAsync(S, (size_t)ld * 8, A + (int64_t)i0 * ld, (size_t)ld * 8, (size_t)cols * 8, (size_t)rows,
+                                    cudaMemcpyDeviceToDevice, st));
+        zero_upper_kernel<<<dim3(rows, cdiv(rows, 256)), 256, 0, st>>>(S, ld, i0, rows);
+        CUGP_CUDA(cudaGetLastError());
+        GemmParams p{};   // own rows: K = rows
+        p.A = S + i0; p.lda = ld;
+        p.B = S; p.ldb = ld;
+        p.C = A + (int64_t)i0 * ld; p.ldc = ld;
+        p.M = rows; p.N = cols; p.K = rows;
+        p.alpha = 1.0; p.beta = 0.0;
+        p.batch = 1;
+        launch_gemm(p, false, false, pick_config(rows, cols, 1, false), st);
+        if (launches) *launches += 2;
+        const int below = n - (i0 + rows);
+        if (below > 0) {
+            GemmParams q{};   // rows below: still T
+            q.A = A + (int64_t)(i0 + rows) * ld + i0; q.lda = ld;
+            q.B = A + (int64_t)(i0 + rows) * ld; q.ldb = ld;
+            q.C = A + (int64_t)i0 * ld; q.ldc = ld;
+            q.M = rows; q.N = cols; q.K = below;
+            q.alpha = 1.0; q.beta = 1.0;
+            q.batch = 1;
+            launch_gemm(q, false, false, pick_config(rows, cols, 1, false), st);
+            if (launches) ++*launches;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // GpBatch
 // ------------------------------------------------------------------------------------------------
@@ -463,7 +563,7 @@ GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(
 GpBatch::~GpBatch() {
     if (st) cudaStreamSynchronize(st);
     dfree(X); dfree(y); dfree(Kb); dfree(invd); dfree(logdet_part); dfree(work); dfree(alpha); dfree(scal);
-    dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout); dfree(tpart); dfree(stepsync); dfree(steppub);
+    dfree(Tb); dfree(Wb); dfree(gradpart); dfree(gradout); dfree(tpart); dfree(stepsync); dfree(steppub); dfree(Wc);
     dfree(Xt); dfree(Ks); dfree(meanpart); dfree(css); dfree(pmean); dfree(pvar); dfree(Xt_all);
     if (hstage) cudaFreeHost(hstage);
     if (hres) cudaFreeHost(hres);
@@ -853,9 +953,48 @@ void GpBatch::loglik(double* ll_out) {
     for (int b = 0; b < B; b++) ll_out[b] = s[(size_t)b * 4 + 2];
 }
 
+// Largest n whose gradient keeps L, L^-1 and K^-1 in three buffers; above it (or when they do not fit the device) the
+// inverse is formed IN PLACE over L (one n x n buffer + n^2 / 4 of scratch): the factor is gone afterwards.
+static int64_t g_inplace_min_n = 60000;
+void set_inplace_inverse_min_n(int64_t v) { g_inplace_min_n = v; }
+
+bool GpBatch::use_inplace_inverse() {
+    if (B != 1 || Bcap != 1) return false;
+    if (n >= g_inplace_min_n) return true;
+    if (Tb && Wb) return false;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+    return (double)free_b < 2.1 * (double)rows_alloc * (double)ld * 8.0;   // Tb + Wb would not fit
+}
+
+void GpBatch::gradient_inplace() {
+    // alpha first (backward sweep over L), then T over L, then K^-1 over T; the trace streams K^-1 from Kb
+    solve();
+    ensure_invd();
+    const size_t need = trtri_inplace_scratch(n), srows = 1024;
+    if (need + srows * (size_t)ld > wc_cap) {
+        sync();
+        dfree(Wc);
+        dalloc(Wc, need + srows * (size_t)ld);
+        wc_cap = need + srows * (size_t)ld;
+    }
+    trtri_inplace(Kb, ld, n, invd, Wc, st, &launches);
+    lauum_inplace(Kb, ld, n, Wc + need, (int)srows, st, &launches);
+    dalloc(gradpart, grad_trace_partials(n, Bcap));
+    launch_grad_trace(X, (int64_t)n * dp, n, dp, h, Kb, ld, mat_stride(), alpha, n, gradpart, gradout, B, st);
+    launches += 2;
+    // Kb no longer holds L: the next request for the factor rebuilds it (alpha and the scalars stay valid)
+    have_L = have_T = have_Kinv = have_Tt = have_invd = false;
+    kinv_in_kb = true;
+}
+
 void GpBatch::gradient_launch() {
     wants_inverse = true;
     factorize();
+    if (!have_Tt && use_inplace_inverse()) {
+        gradient_inplace();
+        return;
+    }
     if (have_Tt) {
         // L^-T and K^-1 = L^-T L^-1 came out of the factorisation: only alpha = L^-T z is left
         solve();

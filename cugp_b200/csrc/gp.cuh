@@ -44,6 +44,11 @@ struct GpBatch {
     double* scal = nullptr;                 // [B][4] quad, logdet, LL
     double *Tb = nullptr, *Wb = nullptr;    // [B][n][ld] lazily: T = L^-1 ; scratch, then Kinv (lower)
     double *gradpart = nullptr, *gradout = nullptr;
+    double* Wc = nullptr;                   // scratch of the in-place inverse (n^2/4 + 1024 rows), large n only
+    size_t wc_cap = 0;
+    bool kinv_in_kb = false;                // the last gradient formed K^-1 over L (in place): Kb is not a factor any more
+    bool use_inplace_inverse();
+    void gradient_inplace();
     double* tpart = nullptr;                // [B][8][n] partial sums of the backward sweep's panel launches
     int* stepsync = nullptr;                // [B][nblk][4] tickets / flags of the fused Cholesky block steps (cholstep.cu)
     double* steppub = nullptr;              // [B][128][132] tile the diagonal CTA of a step publishes for its row tiles
@@ -156,6 +161,10 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
                    int rhs_rows = 0, FusedCtx* fx = nullptr);
 // true: an n x n factorisation of `batch` matrices takes the fused block-step path (outer width 128, batch small enough)
 bool fused_step_applies(int n, int batch);
+void set_inplace_inverse_min_n(int64_t v);   // gradients at n >= v form K^-1 in place over L (default 60 000)
+size_t trtri_inplace_scratch(int n);
+void trtri_inplace(double* A, int64_t ld, int n, const double* invd, double* Wc, cudaStream_t st, long* launches);
+void lauum_inplace(double* A, int64_t ld, int n, double* S, int ib, cudaStream_t st, long* launches);
 void set_idrows_max_n(int n);   // largest n whose factorisation carries the identity rows (0: never)
 int idrows_max_n();
 void set_pred_chunk(int v); // > 0: cap on the test points one prediction chunk carries (0: by memory)

@@ -139,6 +139,8 @@ __device__ __forceinline__ double se_kernel(double d2, const Hyper& h) {
     return h.sf2 * exp(FAST ? d2 * h.neg_half_inv_ell_sq : __ddiv_rn(__dmul_rn(-d2, 0.5), h.ell_sq));
 }
 
+// (68 registers: three CTAs per SM, 36 % occupancy, FP64 pipe 70 % and issue slots 67 % busy, profiles/r2_ncu_summaries.txt;
+// forcing four CTAs per SM -- 64 registers, a few spills -- changed nothing: 2.34 vs 2.36 ms at n = 40 000)
 template <int MODE, bool FAST>
 __global__ void __launch_bounds__(COV_THREADS) cov_tile_kernel(const CovArgs p) {
     extern __shared__ __align__(16) double smem[];

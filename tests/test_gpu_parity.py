@@ -537,6 +537,37 @@ def test_c3_size_properties():
     assert_pred(mu, var, kst @ a, sf2 + sn2 - (v * v).sum(0), yscale=1.0, rtol=1e-8)
 
 
+@pytest.mark.parametrize("n", [130, 700, 3000, 5200])
+def test_inplace_inverse_matches_three_buffer_path(n):
+    """Large-n gradient path (default from n = 60 000: three n x n buffers no longer fit next to each other): T = L^-1 over
+    L with a compact scratch, K^-1 = T^T T over T row block by row block (matrixops.cpp:383-435 in one buffer).  Forced
+    here at small n and compared with the three-buffer path; the factor is rebuilt transparently afterwards."""
+    from cugp_b200.loaders import synthetic_sine
+    X, y = synthetic_sine(n, 10, seed=n)
+    try:
+        lib().cugp_set_tuning(b"idrows_max_n", 0)          # (handles created below keep L^-T out of the factorisation)
+        g = cg.Covsum(n, 10)
+        g.set_data(X, y)
+        g.set_loghyperparam(TH_B)
+        ll0, g0 = g.loglik_resident(), g.grad_resident()
+        lib().cugp_set_tuning(b"inplace_inverse_min_n", 0)
+        g.set_loghyperparam([TH_B[0], TH_B[1], TH_B[2] + 1e-13])
+        ll1, g1 = g.loglik_resident(), g.grad_resident()
+        a1 = g.alpha_resident()
+        ll2 = g.loglik_resident()                          # K^-1 sits where L was: asking again must still be right
+        mu, var = g.compute_test_means_and_variances(X, y, X[:5])
+    finally:
+        lib().cugp_set_tuning(b"inplace_inverse_min_n", 60000)
+        lib().cugp_set_tuning(b"idrows_max_n", 2048)
+    assert_ll(ll1, ll0, 1e-11)
+    assert ll2 == ll1
+    assert_grad(g1, g0, 1e-9)
+    K = PORT.K_train(X, TH_B)
+    assert np.linalg.norm(K @ a1 - y) <= 1e-9 * np.linalg.norm(y)
+    assert np.all(np.isfinite(mu)) and np.all(var > 0)
+    g.close()
+
+
 def test_residual_beyond_int32_indexing():
     """n = 50 000 > 46 341: n * n no longer fits a 32-bit int -- where the reference's GPU flavour indexes with `int`
     (cuda_src/cuda_gp.cu:613-642).  The reference printed a Cholesky residual after every factorisation
