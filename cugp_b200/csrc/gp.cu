@@ -52,7 +52,9 @@ void set_graph_max_n(int n) { g_graph_max_n = n; bump_tuning_epoch(); }
 // leaves SMs idle.  Measured (profiles/r1_overlap_inverse.txt, LL + gradient per evaluation): n = 3000 3.02 -> 2.68 ms,
 // 4096 4.54 -> 4.22, 6000 10.45 -> 10.06, 8192 21.0 -> 22.0 (slower), 16 x 1500 3.75 -> 3.60.  Capping the background
 // GEMMs to fewer SMs (32 / 64 / 96) only made the background the bottleneck, so the default cap is the whole chip.
-static int g_overlap_max_n = 6144, g_overlap_cap = 148;
+// Round 2 (fused steps: the chain is twice as fast and leaves less idle time): n = 2500 1.66 -> 1.54 ms, 3000 2.19 -> 2.22,
+// 4096 3.78 -> 4.12, 6000 9.40 -> 10.01 (profiles/r2_overlap_inverse.txt): the bound moved down to 2800.
+static int g_overlap_max_n = 2800, g_overlap_cap = 148;
 void set_overlap_inverse(int max_n, int cap) {
     if (max_n >= 0) g_overlap_max_n = max_n;
     if (cap > 0) g_overlap_cap = cap;
@@ -264,8 +266,8 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
         const int J0 = J * kDiag, Jend = std::min(n, J0 + kDiag), Jend2 = std::min(n, Jend + kDiag);
         if (J >= 2) CUGP_CUDA(cudaStreamWaitEvent(s2, evU(J - 2), 0));
         step(J0, J > 0, s2);
+        CUGP_CUDA(cudaEventRecord(evP(J), s2));                // "block column J is final" (also for the overlapped inverse)
         if (Jend2 >= n && !(id_rows && fx->kinv)) continue;   // nothing right of block J+1
-        CUGP_CUDA(cudaEventRecord(evP(J), s2));
         CUGP_CUDA(cudaStreamWaitEvent(st, evP(J), 0));
         if (Jend2 < n) {
             potrf_trailing(A, ld, sA, rows_at(Jend), J0, Jend, Jend2, n, batch, st, launches, prof);   // U2(J)
@@ -275,6 +277,7 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
     }
     CUGP_CUDA(cudaEventRecord(ev_end, s2));
     CUGP_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
+    if (nblk == nblk_stride) la->panel_events = true;   // ev[2J] = "block column J is final" (outer width 128)
 }
 
 static int g_adaptive_nb = 0;   // (measured slower, profiles/r2_adaptive_nb.txt: the last wide panel loses its overlap) 1: the outer width follows the REMAINING size; its last part takes the fused 128 path
@@ -760,6 +763,7 @@ void GpBatch::potrf_with_rhs() {
 // 128x128 inverses of L's diagonal blocks: a by-product of the round-1 launch chain, one extra launch after the fused
 // steps -- paid only by the paths that need them (backward sweep, TRTRI recursion).
 void GpBatch::ensure_invd() {
+    if (invd_on_st3) join_T();   // the overlapped inverse is producing them on the third stream
     if (have_invd) return;
     launch_trtri_diag(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, B, st);
     launches++;
@@ -789,6 +793,10 @@ void GpBatch::join_T() {
     if (!t_inflight) return;
     CUGP_CUDA(cudaStreamWaitEvent(st, ev_T, 0));
     t_inflight = false;
+    if (invd_on_st3) {
+        have_invd = true;
+        invd_on_st3 = false;
+    }
 }
 
 // T = L^-1 in row groups of 512, each enqueued on a third stream behind the event "the panel holding the group's last
@@ -810,6 +818,10 @@ void GpBatch::enqueue_trtri_overlapped() {
     for (int r0 = 0; r0 < n; r0 += G) {
         const int r1 = std::min(n, r0 + G), rows = r1 - r0;
         CUGP_CUDA(cudaStreamWaitEvent(st3, la.ev[2 * ((r1 - 1) / NB)], 0));
+        if (!have_invd) {   // fused steps leave no 128x128 inverses behind: this group's, from its finished diagonal blocks
+            launch_trtri_diag(Kb, ld, mat_stride(), n, invd, sI, B, st3, r0 / kDiag, cdiv(r1 - r0, kDiag));
+            launches++;
+        }
         const int cap = r1 == n ? 0 : g_overlap_cap;
         const int64_t o = (int64_t)r0 * (ld + 1);
         trtri_recursive(Kb + o, Tb + o, Wb + o, ld, mat_stride(), rows, invd + (int64_t)(r0 / kDiag) * kDiag * kDiag, sI, B, st3,
@@ -842,6 +854,7 @@ void GpBatch::enqueue_trtri_overlapped() {
     CUGP_CUDA(cudaEventRecord(ev_T, st3));
     t_inflight = true;
     t_valid = true;
+    invd_on_st3 = !have_invd;   // complete once the third stream is joined
 }
 
 void GpBatch::factorize() {
@@ -851,7 +864,7 @@ void GpBatch::factorize() {
     potrf_with_rhs();
     have_L = true;
     // a batch that has computed gradients / predictions before (T exists) will want T = L^-1 again: start it now
-    if (Tb && Wb && la.panel_events && have_invd && !have_Tt && n <= g_overlap_max_n) enqueue_trtri_overlapped();
+    if (Tb && Wb && la.panel_events && !have_Tt && n <= g_overlap_max_n) enqueue_trtri_overlapped();
 }
 
 // alpha = L^-T z.  With T = L^-1 at hand (gradient / prediction paths) it is one streaming pass alpha = T^T z;

@@ -86,6 +86,7 @@ struct GpBatch {
     cudaStream_t st3 = nullptr;
     cudaEvent_t ev_T = nullptr;
     bool t_inflight = false, t_valid = false;
+    bool invd_on_st3 = false;              // the overlapped inverse also produces the 128x128 diagonal inverses
     void enqueue_trtri_overlapped();
     void join_T();                         // main stream waits for the third stream
     // CUDA graphs of the theta-independent launch chains (small and medium n are bound by the chain of dependent

@@ -458,8 +458,8 @@ __device__ __forceinline__ void cta_gemm8(int mb, int nbk, bool lower, FA A, FB 
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
     potrf_diag_blocked_kernel(double* A, int64_t ld, int64_t sA, int n, int j0, double* invd, int64_t sInvd,
                               double* logdet_part, int nblk, int blk, int factor, long long* prof) {
-    if (blk < 0) {   // one launch over every diagonal block: blockIdx.y selects it
-        blk = blockIdx.y;
+    if (blk < 0) {   // one launch over a range of diagonal blocks: blockIdx.y selects it, -1 - blk is the first one
+        blk = blockIdx.y + (-1 - blk);
         j0 = blk * kDiag;
         invd += (int64_t)blk * kDiag * kDiag;
     }
@@ -1172,16 +1172,18 @@ void debug_diag_phases(double* A, int64_t ld, int n, double* invd, double* logde
 }
 
 void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* invd, int64_t sInvd, int batch,
-                       cudaStream_t st) {
+                       cudaStream_t st, int blk0, int nblocks) {
     constexpr size_t smem = (size_t)(DB * DLD + 64 * TLD + DB + 2 * SB + DB) * sizeof(double);
     static bool configured = false;
     if (!configured) {
         CUGP_CUDA(cudaFuncSetAttribute(potrf_diag_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    // one launch, blockIdx.y = diagonal block
-    potrf_diag_blocked_kernel<<<dim3(batch, cdiv(n, DB)), DIAG_THREADS, smem, st>>>(const_cast<double*>(L), ld, sL, n, 0, invd,
-                                                                                     sInvd, nullptr, 0, -1, 0, nullptr);
+    // one launch, blockIdx.y = diagonal block (blk0 ..)
+    if (nblocks <= 0) nblocks = cdiv(n, DB) - blk0;
+    if (nblocks <= 0) return;
+    potrf_diag_blocked_kernel<<<dim3(batch, nblocks), DIAG_THREADS, smem, st>>>(const_cast<double*>(L), ld, sL, n, 0, invd,
+                                                                                 sInvd, nullptr, 0, -1 - blk0, 0, nullptr);
     CUGP_CUDA(cudaGetLastError());
 }
 

@@ -58,7 +58,7 @@ void launch_potrf_diag(double* A, int64_t ld, int64_t sA, int n, int j0, double*
 
 // inverses of the 128x128 diagonal blocks of a given lower-triangular L (no factorisation): feeds trtri_recursive
 void launch_trtri_diag(const double* L, int64_t ld, int64_t sL, int n, double* invd, int64_t sInvd, int batch,
-                       cudaStream_t st);
+                       cudaStream_t st, int blk0 = 0, int nblocks = 0 /* 0: all from blk0 */);
 void debug_diag_phases(double* A, int64_t ld, int n, double* invd, double* logdet, long long* stamps_dev, cudaStream_t st);
 
 // ---- K3: alpha = L^-T z.  (The forward substitution is fused into the Cholesky, gp.cu.)

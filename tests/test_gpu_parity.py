@@ -334,7 +334,7 @@ def test_goldens_hold_with_the_reference_arithmetic_too():
 
 
 # ---------------------------------------------------------------------------------------------- golden cases
-OVERLAP_DEFAULT = 6144   # library default of the tuning key overlap_inv_max_n
+OVERLAP_DEFAULT = 2800   # library default of the tuning key overlap_inv_max_n
 
 COVSUM = [n for n, c in GOLD.items() if c["kind"] == "covsum"]
 BCMS = [n for n, c in GOLD.items() if c["kind"] == "bcm"]
