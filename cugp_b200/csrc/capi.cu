@@ -167,6 +167,12 @@ int cugp_set_tuning(const char* key, long value) {
         set_adaptive_nb(value != 0);
         return CUGP_OK;
     }
+    if (std::strcmp(key, "step_rows_tile") == 0) {
+        if (value != 0 && value != 32 && value != 64) return CUGP_ERR_INVALID;
+        set_step_rows_tile((int)value);
+        bump_tuning_epoch();
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "fused_panel") == 0) {
         set_fused_panel(value != 0);
         return CUGP_OK;

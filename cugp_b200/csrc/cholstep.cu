@@ -271,6 +271,7 @@ struct StepArgs {
     int* sync;             // [batch][nblk][4]: ticket, SYRKD counter, DIAG column slabs published (0..4)
     int prologue;
     int nrow_tiles;
+    int rt;                // rows per ROWS tile: 32 or 64
     int roles;             // 0: every role in this launch; 1: SYRKD + DIAG only; 2: ROWS only (DIAG's launch is complete)
     long long* stamps;
 };
@@ -296,6 +297,124 @@ __device__ __forceinline__ void publish_slab(const double* S, double* pub, doubl
             else if (c == i) dst[0] = v.x;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ROWS with 64-row tiles (StepArgs::rt == 64): half as many CTAs sit on SMs waiting for DIAG's flags, so the trailing
+// updates of the previous step (other stream) keep more of the chip.  The 64x128 tile takes the As+Cs region; the
+// prologue's operands go through the (still unused) Lb region in two K-halves of 64 (stride 68: 68 % 16 == 4).
+// ------------------------------------------------------------------------------------------------
+constexpr int RT64 = 64;
+constexpr int LDH_ = DB / 2 + 4;    // 68
+__device__ __forceinline__ void load_half(double* dst, const double* src, int64_t ld, int rows, int rows_valid, int tid,
+                                          const double* safe) {
+    for (int e = tid; e < rows * (DB / 4); e += NT) {
+        const int r = e >> 5, c = (e & 31) * 2;
+        const int bytes = r < rows_valid ? 16 : 0;
+        cp_async16(dst + r * LDH_ + c, bytes ? src + (int64_t)r * ld + c : safe, bytes);
+    }
+}
+
+template <class STAMP>
+__device__ __forceinline__ void rows64_role(const StepArgs& p, double* A, const double* pub, int* sync, double* Lb, double* Ct,
+                                            int tile, int j0, int nb, int tid, STAMP stamp) {
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    const int r0 = j0 + nb + tile * RT64;
+    const int rows_valid = p.nrows - r0;
+    load_tile(Ct, A + (int64_t)r0 * p.ld + j0, p.ld, RT64, rows_valid, nb, tid, A);
+    if (p.prologue) {
+        double* Pa = Lb;                    // [64][68]  L[R, prev half]
+        double* Pb = Lb + RT64 * LDH_;      // [128][68] L[block rows, prev half]
+        const int pj = j0 - DB;
+        // C[64 x 128] -= L[R, prev] L[block rows, prev]^T : warp tile 16 x 32, K = 2 x 64
+        const int wr = (warp >> 2) * 16, wc = (warp & 3) * 32;
+        double acc[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            if (h) __syncthreads();   // every warp is done with the first half
+            load_half(Pa, A + (int64_t)r0 * p.ld + pj + h * (DB / 2), p.ld, RT64, rows_valid, tid, A);
+            load_half(Pb, A + (int64_t)j0 * p.ld + pj + h * (DB / 2), p.ld, DB, nb, tid, A);
+            cp_async_wait_all();
+            __syncthreads();
+            if (h == 0) stamp(1);
+            warp_mma<2, 4>(acc, 0, DB / 2, [&](int i, int k) { return Pa[(wr + i) * LDH_ + k]; },
+                           [&](int k, int j) { return Pb[(wc + j) * LDH_ + k]; }, lane);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double* dst = Ct + (wr + i * 8 + g) * LDS_ + wc + j * 8 + 2 * q;
+                dst[0] -= acc[i][j][0];
+                dst[1] -= acc[i][j][1];
+            }
+    } else {
+        cp_async_wait_all();
+    }
+    __syncthreads();   // Lb is free again, Ct holds the updated tile
+    stamp(2);
+    // as the 32-row form below, two 8x8 blocks (rows r8 and r8 + 32) per warp
+    const int r8 = (warp >> 2) * 8, c8 = (warp & 3) * 8;
+    for (int c = 0; c < DB / SBW; c++) {
+        const int c0 = c * SBW;
+        if (c0 >= nb) break;
+        if (tid == 0)
+            while (ld_acquire(&sync[2]) <= c) __nanosleep(20);
+        __syncthreads();
+        stamp(3 + c);
+        for (int e = tid; e < (DB - c0) * SLAB_CH; e += NT) {
+            const int i = c0 + e / SLAB_CH, cc = c0 + 2 * (e % SLAB_CH);
+            cp_async16(Lb + i * LDS_ + cc, pub + i * LDS_ + cc, 16);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        double x[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        for (int k = 0; k < c8 + 8; k += 4) {
+            const double t = k + q <= c8 + g ? Lb[(c0 + k + q) * LDS_ + c0 + c8 + g + 1] : 0.0;
+            dmma(x[0][0], x[0][1], Ct[(r8 + g) * LDS_ + c0 + k + q], t);
+            dmma(x[1][0], x[1][1], Ct[(r8 + 32 + g) * LDS_ + c0 + k + q], t);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            Ct[(r8 + 32 * h + g) * LDS_ + c0 + c8 + 2 * q] = x[h][0];
+            Ct[(r8 + 32 * h + g) * LDS_ + c0 + c8 + 2 * q + 1] = x[h][1];
+        }
+        __syncthreads();
+        // columns c0 .. c0+31 of these rows are final: they go home now, in the shadow of DIAG's next slab
+        for (int e = tid; e < RT64 * (SBW / 2); e += NT) {
+            const int r = e >> 4, cc = c0 + (e & 15) * 2;
+            if (r < rows_valid) {
+                double* dst = A + (int64_t)(r0 + r) * p.ld + j0 + cc;
+                if (cc + 1 < nb) *reinterpret_cast<double2*>(dst) = make_double2(Ct[r * LDS_ + cc], Ct[r * LDS_ + cc + 1]);
+                else if (cc < nb) dst[0] = Ct[r * LDS_ + cc];
+            }
+        }
+        for (int c1 = c0 + SBW; c1 < nb; c1 += SBW) {
+            double a[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, bb[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int k = 0; k < SBW; k += 8) {
+                const double l0 = Lb[(c1 + c8 + g) * LDS_ + c0 + k + q], l1 = Lb[(c1 + c8 + g) * LDS_ + c0 + k + 4 + q];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    dmma(a[h][0], a[h][1], Ct[(r8 + 32 * h + g) * LDS_ + c0 + k + q], l0);
+                    dmma(bb[h][0], bb[h][1], Ct[(r8 + 32 * h + g) * LDS_ + c0 + k + 4 + q], l1);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                double* dst = Ct + (r8 + 32 * h + g) * LDS_ + c1 + c8 + 2 * q;   // this warp's own blocks
+                dst[0] -= a[h][0] + bb[h][0];
+                dst[1] -= a[h][1] + bb[h][1];
+            }
+        }
+    }
+    stamp(7);
+    stamp(8);
 }
 
 __global__ void __launch_bounds__(NT, 1) chol_step_kernel(const StepArgs p) {
@@ -487,6 +606,13 @@ __global__ void __launch_bounds__(NT, 1) chol_step_kernel(const StepArgs p) {
     // ---------------------------------------------------------------------- ROWS
     const int tile = ticket - nsy - 1;
     if (tile >= p.nrow_tiles) return;
+    if (p.rt == RT64) {
+        if (tile == 0) STEP_STAMP(2, 0);
+        rows64_role(p, A, pub, sync, Lb, As, tile, j0, nb, tid, [&](int idx) {
+            if (tile == 0) STEP_STAMP(2, idx);
+        });
+        return;
+    }
     const int r0 = j0 + nb + tile * SBW;          // first row of the tile (rows below the diagonal block)
     const int rows_valid = p.nrows - r0;
     const bool st0 = tile == 0;
@@ -576,9 +702,24 @@ static long long* g_step_stamps = nullptr;
 
 void set_step_stamps(long long* dev) { g_step_stamps = dev; }
 size_t chol_step_pub_doubles(int batch) { return (size_t)batch * DB * LDS_; }
-int chol_step_ctas(int n, int nrows, int j0) {
+static int g_rows_tile = 0;   // 0: by CTA count (below), else forced 32 / 64
+void set_step_rows_tile(int rows) { g_rows_tile = rows == 32 ? 32 : rows == 64 ? 64 : 0; }
+int step_rows_tile() { return g_rows_tile; }
+// 64-row tiles once the step's CTAs would take more than half the chip (the tiles wait on their SMs for DIAG while the
+// previous step's trailing update runs on the other stream); below that the 32-row form ends ~3 us earlier per step.
+// profiles/r2_rows_tile.txt: n = 2048 LL+gradient 0.80 -> 0.73 ms, 4096 3.78 -> 3.65, two 1500-row experts 0.74 -> 0.66.
+static int pick_rows_tile(int below, int batch) {
+    if (g_rows_tile) return g_rows_tile;
+    static const int sms = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
+    return (int64_t)batch * (NSYRKD + 1 + cdiv(std::max(below, 0), SBW)) > sms / 2 ? 64 : 32;
+}
+int chol_step_ctas(int n, int nrows, int j0, int batch) {
     const int nb = std::min(DB, n - j0), below = nrows - (j0 + nb);
-    return NSYRKD + 1 + (below > 0 ? cdiv(below, SBW) : 0);
+    return NSYRKD + 1 + (below > 0 ? cdiv(below, pick_rows_tile(below, batch)) : 0);
 }
 
 void launch_chol_step(double* A, int64_t ld, int64_t sA, int n, int nrows, int j0, double* pub, double* logdet_part, int nblk,
@@ -594,7 +735,8 @@ void launch_chol_step(double* A, int64_t ld, int64_t sA, int n, int nrows, int j
     p.sync = sync; p.prologue = prologue; p.stamps = g_step_stamps;
     const int nb = std::min(DB, n - j0);
     const int below = nrows - (j0 + nb);
-    p.nrow_tiles = below > 0 ? cdiv(below, SBW) : 0;
+    p.rt = pick_rows_tile(below, batch);
+    p.nrow_tiles = below > 0 ? cdiv(below, p.rt) : 0;
     p.roles = roles;
     const int head = (prologue ? NSYRKD : 0) + 1;
     const int ctas = roles == 1 ? head : roles == 2 ? p.nrow_tiles : head + p.nrow_tiles;

@@ -14,8 +14,11 @@ void launch_chol_step(double* A, int64_t ld, int64_t sA, int n, int nrows, int j
                       int* sync, int prologue, int batch, cudaStream_t st, int roles = 0);
 // roles = 0: one launch (the row tiles wait for the diagonal CTA on their SMs: only when every CTA of the launch is
 // resident at once); roles = 1 then roles = 2: diagonal part, then the row tiles, as two launches (wide batches).
-int chol_step_ctas(int n, int nrows, int j0);   // CTAs per matrix of a roles = 0 launch
+int chol_step_ctas(int n, int nrows, int j0, int batch);   // CTAs per matrix of a roles = 0 launch of `batch` matrices
 size_t chol_step_pub_doubles(int batch);
+// Rows per ROWS tile: 0 (default) = by CTA count, or forced 32 / 64.  Fewer, taller tiles = fewer CTAs waiting on SMs.
+void set_step_rows_tile(int rows);
+int step_rows_tile();
 
 // Tuning aid: device buffer [nblk][3][16] of globaltimer stamps written by every step (nullptr: off).
 void set_step_stamps(long long* dev);

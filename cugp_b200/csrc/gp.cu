@@ -120,7 +120,7 @@ static void potrf_panel(double* A, int64_t ld, int64_t sA, int n, int nrows, int
         if (fused) {
             // diagonal block (slab factorisation, 32x32 inverses) and the TRSM of every row below in the fused step kernel
             // (cholstep.cu) without its prologue: one launch while its CTAs fit the chip together, else two
-            const bool split = (int64_t)batch * chol_step_ctas(n, nrows, j0) > sms;
+            const bool split = (int64_t)batch * chol_step_ctas(n, nrows, j0, batch) > sms;
             if (!split) {
                 launch_chol_step(A, ld, sA, n, nrows, j0, fx->pub, logdet_part, nblk, fx->sync, 0, batch, st, 0);
                 if (launches) ++*launches;
@@ -229,7 +229,7 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
     const int base_rows = nrows - id_rows;
     auto rows_at = [&](int Jend) { return base_rows + std::min(id_rows, Jend); };
     int widest = 0;
-    for (int J0 = 0; J0 < n; J0 += kDiag) widest = std::max(widest, chol_step_ctas(n, rows_at(std::min(n, J0 + kDiag)), J0));
+    for (int J0 = 0; J0 < n; J0 += kDiag) widest = std::max(widest, chol_step_ctas(n, rows_at(std::min(n, J0 + kDiag)), J0, batch));
     const bool split = (int64_t)batch * widest > sms;
     auto step = [&](int J0, int prologue, cudaStream_t s) {
         const int nr = rows_at(std::min(n, J0 + kDiag));
