@@ -173,6 +173,19 @@ int cugp_set_tuning(const char* key, long value) {
         bump_tuning_epoch();
         return CUGP_OK;
     }
+    if (std::strcmp(key, "kinv_stream") == 0) {
+        set_kinv_stream(value != 0);
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "fused_gemm_cap") == 0) {
+        set_fused_gemm_cap((int)value);
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "kinv_group") == 0) {
+        if (value < 1) return CUGP_ERR_INVALID;
+        set_kinv_group((int)value);
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "fused_panel") == 0) {
         set_fused_panel(value != 0);
         return CUGP_OK;

@@ -100,6 +100,14 @@ bool fused_step_applies(int n, int batch) {
 // One outer panel [J0, Jend): right-looking over its 128-column blocks, full height, updates confined to the panel.
 // `nrows` >= n: rows n.. of A are appended right-hand sides (y^T): they ride through the TRSM and the updates like
 // any other row below the diagonal, which performs the forward substitution L z = y for free (z^T ends up in row n).
+static int g_kinv_stream = 0;   // 1: identity-row path accumulates K^-1 on the third stream -- SLOWER (profiles/r2_kinv_stream.txt:
+// two experts 0.66 -> 0.74 ms, n = 2048 0.72 -> 0.93: its CTAs take the SMs the next step's launch needs)
+void set_kinv_stream(int v) { g_kinv_stream = v; bump_tuning_epoch(); }
+static int g_fused_gemm_cap = 0;   // (measured slower, profiles/r2_kinv_stream.txt) > 0: the fused path's main-stream GEMMs leave the step launch's SMs alone (at least this many SMs stay theirs)
+void set_fused_gemm_cap(int v) { g_fused_gemm_cap = v; bump_tuning_epoch(); }
+static int g_kinv_group = 1;   // identity-row path: K^-1 accumulated every this many block columns; > 1 measured slower
+// (profiles/r2_kinv_stream.txt: the bigger bursts delay U2 and the last one cannot hide behind the chain)
+void set_kinv_group(int v) { g_kinv_group = v; bump_tuning_epoch(); }
 static int g_fused_panel = 1;   // outer width > 128: the diagonal block + TRSM of every 128-column block as the fused step
 void set_fused_panel(int v) { g_fused_panel = v; bump_tuning_epoch(); }
 
@@ -163,7 +171,7 @@ static void potrf_panel(double* A, int64_t ld, int64_t sA, int n, int nrows, int
 
 // A[c0:, c0:c1] -= P[c0:, :] P[c0:c1, :]^T with P = L[:, J0:Jend] (lower trapezoid; c1 == n: the whole trailing block)
 static void potrf_trailing(double* A, int64_t ld, int64_t sA, int nrows, int J0, int Jend, int c0, int c1, int batch,
-                           cudaStream_t st, long* launches, GpBatch::Prof* prof) {
+                           cudaStream_t st, long* launches, GpBatch::Prof* prof, int cap_sms = 0) {
     const int m = nrows - c0, w = c1 - c0;
     if (m <= 0 || w <= 0) return;
     GemmParams q{};
@@ -175,7 +183,9 @@ static void potrf_trailing(double* A, int64_t ld, int64_t sA, int nrows, int J0,
     q.batch = batch;
     q.lower_tiles = 1;
     if (prof) CUGP_CUDA(cudaEventRecord(prof_event(prof), st));
-    launch_gemm(q, true, true, pick_config(m, w, batch, true), st);
+    const GemmConfig cfg = pick_config(m, w, batch, true);
+    if (cap_sms > 0) q.max_ctas = cfg == GEMM_BIG ? cap_sms : 2 * cap_sms;
+    launch_gemm(q, true, true, cfg, st);
     if (prof) {
         CUGP_CUDA(cudaEventRecord(prof_event(prof), st));
         // lower trapezoid, 2 flop per MAC: w(w+1)/2 + (m-w)w outputs
@@ -200,8 +210,15 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
     fx->invd_done = false;   // the 128x128 inverses of the diagonal blocks are not a by-product here: GpBatch::ensure_invd
     // With the identity rows, column block J of U = L^-T (rows < Jend) is final after step(J): K^-1 = U U^T is accumulated
     // block column by block column on the main stream, in the chain's shadow, instead of one LAUUM launch after it.
+    int cap_sms = 0;   // set below (look-ahead only): SMs the main stream's GEMMs may hold while the chain runs
+    // ... in groups of g_kinv_group block columns: nothing reads K^-1 before the end, and a K = 256 / 384 update reads and
+    // writes the accumulator half / a third as often (rows >= a block column's own Jend of U are still zero)
+    const int kgroup = std::max(1, g_kinv_group);
     auto kinv_update = [&](int J0, int Jend, cudaStream_t s) {
         if (!id_rows || !fx->kinv) return;
+        const int J = J0 / kDiag;
+        if ((J + 1) % kgroup != 0 && Jend < n) return;    // not the last block column of its group
+        J0 = J / kgroup * kgroup * kDiag;
         GemmParams q{};
         const double* U = A + (int64_t)(n + 1) * ld + J0;     // identity rows start below the right-hand-side row
         q.A = U; q.lda = ld; q.sA = sA;
@@ -211,7 +228,9 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
         q.alpha = 1.0; q.beta = 1.0;
         q.batch = batch;
         q.lower_tiles = 1;
-        launch_gemm(q, true, true, pick_config(Jend, Jend, batch, true), s);
+        const GemmConfig cfg = pick_config(Jend, Jend, batch, true);
+        if (cap_sms > 0) q.max_ctas = cfg == GEMM_BIG ? cap_sms : 2 * cap_sms;
+        launch_gemm(q, true, true, cfg, s);
         if (launches) ++*launches;
     };
     if (nblk == nblk_stride)   // (a trailing sub-matrix: the caller has zeroed the whole array)
@@ -251,6 +270,7 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
         }
         return;
     }
+    if (g_fused_gemm_cap > 0 && !split) cap_sms = std::max(g_fused_gemm_cap, sms - batch * widest);
     cudaStream_t s2 = la->st2;
     while ((int)la->ev.size() < 2 * nblk + 2) {
         cudaEvent_t e;
@@ -267,16 +287,27 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
         if (J >= 2) CUGP_CUDA(cudaStreamWaitEvent(s2, evU(J - 2), 0));
         step(J0, J > 0, s2);
         CUGP_CUDA(cudaEventRecord(evP(J), s2));                // "block column J is final" (also for the overlapped inverse)
-        if (Jend2 >= n && !(id_rows && fx->kinv)) continue;   // nothing right of block J+1
+        // K^-1 += U[:, J] U[:, J]^T has no reader before the end: on its own stream it fills the gaps U2 leaves instead of
+        // delaying U2(J+1) (two experts per GPU: the main stream's GEMMs, not the chain, set the pace)
+        cudaStream_t sk = id_rows && fx->kinv && fx->kinv_stream && fx->kinv_done ? fx->kinv_stream : nullptr;
+        if (sk) {
+            CUGP_CUDA(cudaStreamWaitEvent(sk, evP(J), 0));
+            kinv_update(J0, Jend, sk);
+        }
+        if (Jend2 >= n && (sk || !(id_rows && fx->kinv) || ((J + 1) % kgroup != 0 && Jend < n))) continue;   // nothing to do on the main stream
         CUGP_CUDA(cudaStreamWaitEvent(st, evP(J), 0));
         if (Jend2 < n) {
-            potrf_trailing(A, ld, sA, rows_at(Jend), J0, Jend, Jend2, n, batch, st, launches, prof);   // U2(J)
+            potrf_trailing(A, ld, sA, rows_at(Jend), J0, Jend, Jend2, n, batch, st, launches, prof, cap_sms);   // U2(J)
             CUGP_CUDA(cudaEventRecord(evU(J), st));
         }
-        kinv_update(J0, Jend, st);
+        if (!sk) kinv_update(J0, Jend, st);
     }
     CUGP_CUDA(cudaEventRecord(ev_end, s2));
     CUGP_CUDA(cudaStreamWaitEvent(st, ev_end, 0));
+    if (id_rows && fx->kinv && fx->kinv_stream && fx->kinv_done) {
+        CUGP_CUDA(cudaEventRecord(fx->kinv_done, fx->kinv_stream));
+        CUGP_CUDA(cudaStreamWaitEvent(st, fx->kinv_done, 0));
+    }
     if (nblk == nblk_stride) la->panel_events = true;   // ev[2J] = "block column J is final" (outer width 128)
 }
 
@@ -585,6 +616,7 @@ GpBatch::~GpBatch() {
         cudaStreamDestroy(st3);
     }
     if (ev_T) cudaEventDestroy(ev_T);
+    if (ev_kinv) cudaEventDestroy(ev_kinv);
     if (own_stream && st) cudaStreamDestroy(st);
 }
 
@@ -746,6 +778,10 @@ void GpBatch::potrf_with_rhs() {
                 CUGP_CUDA(cudaMemsetAsync(Wb + (int64_t)b * mat_stride(), 0, (size_t)n * ld * sizeof(double), st));
         }
         FusedCtx fx{stepsync, steppub, id ? n : 0, id ? Wb : nullptr, false};
+        if (id && g_kinv_stream) {
+            fx.kinv_stream = st3;
+            fx.kinv_done = ev_kinv;
+        }
         potrf_blocked(Kb, ld, mat_stride(), n, invd, (int64_t)nblk * kDiag * kDiag, logdet_part, B, st, &launches, &prof, &la,
                       id ? 1 + n : 1, &fx);
         have_invd = fx.invd_done;
@@ -754,6 +790,7 @@ void GpBatch::potrf_with_rhs() {
         launches += 2;
     };
     if (id) ensure_TW();
+    if (id && g_kinv_stream) ensure_st3();
     have_invd = !g_fused_step || B > g_fused_max_batch;     // what a replayed graph leaves behind
     if (!run_graphed(id ? graph_potrf_id : graph_potrf_rhs, body)) body();
     have_Tt = id;
@@ -805,13 +842,17 @@ void GpBatch::join_T() {
 // of 128-column block steps (n <~ 6000: 2.5 ms for 0.65 ms worth of flops at n = 4096) the other SMs do this work; the
 // GEMMs are capped to g_overlap_cap CTAs so the chain's high-priority launches always find free SMs.  The last group
 // can only start when the chain has ended and runs uncapped.
+void GpBatch::ensure_st3() {
+    if (st3) return;
+    CUGP_CUDA(cudaStreamCreateWithFlags(&st3, cudaStreamNonBlocking));
+    CUGP_CUDA(cudaEventCreateWithFlags(&ev_T, cudaEventDisableTiming));
+    CUGP_CUDA(cudaEventCreateWithFlags(&ev_kinv, cudaEventDisableTiming));
+}
+
 void GpBatch::enqueue_trtri_overlapped() {
     const int NB = potrf_outer_width(n);
     constexpr int G = 512;
-    if (!st3) {
-        CUGP_CUDA(cudaStreamCreateWithFlags(&st3, cudaStreamNonBlocking));
-        CUGP_CUDA(cudaEventCreateWithFlags(&ev_T, cudaEventDisableTiming));
-    }
+    ensure_st3();
     const int64_t sI = (int64_t)nblk * kDiag * kDiag;
     // (Accumulating K^-1 = sum_g T[g, :]^T T[g, :] behind every finished group as well was measured and dropped: n = 4096
     // 4.22 -> 4.48 ms, n = 6000 10.06 -> 10.76 ms -- more background CTAs delay the chain more than the LAUUM they hide.)

@@ -26,6 +26,8 @@ struct FusedCtx {
     int id_rows;        // > 0: that many identity rows follow the right-hand-side rows (they leave as L^-T)
     double* kinv;       // with id_rows: K^-1 = L^-T L^-1 is accumulated here (lower triangle, zeroed by the caller); may be null
     bool invd_done;     // out: the 128x128 inverses of the diagonal blocks were produced (round-1 chain) or not (fused)
+    cudaStream_t kinv_stream = nullptr;   // with kinv and look-ahead: the K^-1 updates run here (joined before returning)
+    cudaEvent_t kinv_done = nullptr;
 };
 
 struct GpBatch {
@@ -85,6 +87,8 @@ struct GpBatch {
     // (see enqueue_trtri_overlapped): t_valid = the work in flight belongs to the current (data, theta).
     cudaStream_t st3 = nullptr;
     cudaEvent_t ev_T = nullptr;
+    cudaEvent_t ev_kinv = nullptr;   // K^-1 accumulation on st3 has been joined up to here
+    void ensure_st3();
     bool t_inflight = false, t_valid = false;
     bool invd_on_st3 = false;              // the overlapped inverse also produces the 128x128 diagonal inverses
     void enqueue_trtri_overlapped();
@@ -171,6 +175,9 @@ int idrows_max_n();
 void set_pred_chunk(int v); // > 0: cap on the test points one prediction chunk carries (0: by memory)
 void set_fused_max_batch(int v);   // widest batch the fused step is used for
 void set_adaptive_nb(int v);  // 1 (default 0: measured slower): outer width by the remaining size, fused 128 path for the last part
+void set_kinv_stream(int v);   // 1: K^-1 accumulation of the identity-row path on its own stream (default 0: measured slower)
+void set_fused_gemm_cap(int v);
+void set_kinv_group(int v);
 void set_fused_panel(int v);  // 1 (default): wider outer panels also factor their 128-column blocks with the fused step
 void set_fused_step(int v); // 1 (default): one fused launch per 128-column block step when the outer width is 128
 // Tuning epoch: bumped by every tuning change so cached graphs are re-captured.  graph_max_n: largest n whose launch
