@@ -41,7 +41,7 @@ TH_B = [3.762111, -1.152105, -0.384461]   # trained values, cuda_src/main.cpp:19
 # the CPU legs time it on the first REF_SAMPLE_N rows of the SAME synthetic set.  ONE size per workload, used by both the
 # `cpu_baseline` leg and `--impl reference`; every CPU line says so (`same_config: false`) -- a flop-rate or
 # evaluation-rate ratio across sizes is a stated baseline, not a like-for-like speed-up.
-REF_SAMPLE_N = {"c5": 2048, "c3": 2048, "c2": 1024, "c4": 1500}
+REF_SAMPLE_N = {"c5": 2048, "c3": 1024, "c2": 1024, "c4": 1500}
 TH_C = [2.0, 2.0, 2.0]                    # cuda_scalingdist/main.cpp:298-301
 NOMINAL_FP64_TFLOPS = 37.0                # HGX B200 data sheet, dense FP64 (tensor = vector)
 
@@ -167,6 +167,22 @@ def cpu_baseline(kind_pref: str, n_s: int, theta, reps: int = 1):
                       f"{best:.2f} s, LL={ll:.6f}; host has {os.cpu_count()} cores, reference is single-threaded"}
 
 
+def cpu_c3_sample(impl, n_s: int):
+    """C3 (train + predict) on a bounded sample: compute_loglikelihood, then compute_test_means_and_variances of n_s test
+    points (the GPU arm's n : m = 1 : 1), with the GPU arm's flop count 2 n^3/3 + n^2 m."""
+    from cugp_b200.loaders import synthetic_sine
+    X, y = synthetic_sine(2 * n_s, 10)
+    Xt, X, y = X[n_s:], X[:n_s], y[:n_s]
+    t = time.perf_counter()
+    impl.loglik(X, y, TH_B)
+    impl.predict(X, y, TH_B, Xt)
+    dt = time.perf_counter() - t
+    fl = 2.0 * n_s ** 3 / 3 + float(n_s) ** 2 * n_s
+    return {"value": fl / dt / 1e12, "unit": "TFLOP/s", "cores": 1, "kind": impl.kind, "same_config": False, "sample_n": n_s,
+            "sample": f"compute_loglikelihood + compute_test_means_and_variances of {n_s} points at n={n_s} (of 10000 / 10000), "
+                      f"theta_B, {dt:.2f} s; flops counted as on the GPU arm (2 n^3/3 + n^2 m)"}, dt
+
+
 def cpu_c4_model(impl, m: int, m_lo: int = 4, m_hi: int = 260):
     """The reference's BCM prediction at the GPU arm's OWN m: every expert pays its training (three factorisations and
     the inverse, covkernel.cpp:277-296) once and then O(n^2) per test point (covkernel.cpp:297-302).  Both parts are
@@ -203,7 +219,9 @@ def run_reference_arm(a):
     model = []
 
     def step():
-        if a.workload in ("c5", "c3"):
+        if a.workload == "c3":
+            model.append(cpu_c3_sample(impl, n_s)[0])
+        elif a.workload == "c5":
             impl.loglik(X, y, TH_B)
         elif a.workload == "c2":
             impl.loglik(X, y, TH_B)
@@ -218,7 +236,12 @@ def run_reference_arm(a):
     for _ in range(a.steps):
         step()
     ms = (time.perf_counter() - t) * 1e3 / a.steps
-    if a.workload in ("c5", "c3"):
+    if a.workload == "c3":
+        metric, unit = "fp64_train_predict_tflops", "TFLOP/s"
+        value = statistics.median(mm["value"] for mm in model)
+        sample = model[-1]["sample"]
+        same = False
+    elif a.workload == "c5":
         metric, unit, value = "fp64_cholesky_tflops", "TFLOP/s", (n_s ** 3 / 3) / (ms * 1e-3) / 1e12
         sample = f"compute_loglikelihood, n={n_s} synthetic rows (of {a.n}), theta_B"
         same = False
@@ -594,6 +617,11 @@ def main():
 
         if a.workload == "c2":
             metric, unit, per_rank, per_rank_e2e = "loglik_grad_evals_per_s", "evals/s", 1e3 / ms, 1e3 / ms_e2e
+        elif a.workload == "c3":
+            # the step is train + predict: Cholesky n^3/3, T = L^-1 n^3/3, V = T K*^T (triangular k-ranges) n^2 m
+            metric, unit = "fp64_train_predict_tflops", "TFLOP/s"
+            fl = 2.0 * n ** 3 / 3 + float(n) ** 2 * a.m
+            per_rank, per_rank_e2e = fl / (ms * 1e-3) / 1e12, fl / (ms_e2e * 1e-3) / 1e12
         else:
             metric, unit = "fp64_cholesky_tflops", "TFLOP/s"
             per_rank, per_rank_e2e = (n ** 3 / 3) / (ms * 1e-3) / 1e12, (n ** 3 / 3) / (ms_e2e * 1e-3) / 1e12
@@ -612,7 +640,9 @@ def main():
                             "solves_gbs": tri_bytes / (ms_solve * 1e-3) / 1e9}   # K3 backward sweep streams L once (the
                                                                                   # forward substitution is fused into K2)
         config = {"workload": {"c5": f"C5 synthetic exact GP n={n} d=10: covariance build + blocked Cholesky + solves + LL",
-                               "c3": f"C3 exact GP n={n} d=10 train + predict {a.m} points",
+                               "c3": f"C3 exact GP n={n} d=10 train + predict {a.m} points per step (flops counted: "
+                                     f"Cholesky n^3/3 + inverse factor n^3/3 + V = L^-1 K*^T n^2 m; the Cholesky alone is "
+                                     f"phases_ms.cholesky_tflops)",
                                "c2": f"C2 exact GP n={n} d=10 hyper-parameter loop: LL + gradient per evaluation"}[a.workload],
                   "n": n, "d": 10, "theta": TH_B, "parallelism": f"replicas x{world} (exact GP does not shard)",
                   "l2": "256 MB flush between steps" if use_flush else "inputs (8 n^2 B) exceed L2"}
@@ -678,9 +708,9 @@ def main():
         achieved = syrk_flops / (syrk_ms * 1e-3) / 1e12
         traffic = traffic_detail = None
         tp = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
-        if os.path.exists(tp):
-            # one ncu --set full capture of ONE launch of this kernel (the first full-width update of an n = 40 000
-            # factorisation): its DRAM bytes next to the algorithmic bytes of that same launch
+        if os.path.exists(tp) and a.workload == "c5":   # the capture is of C5's own first full-width update
+            # one ncu capture of ONE launch of this kernel (the first full-width update of C5 itself): its DRAM bytes next to
+            # the algorithmic bytes of that same launch
             traffic_detail = json.load(open(tp))
             traffic = traffic_detail.get("dram_bytes_total")
         out["roofline"] = {"bound": "tensor", "kernel": "dgemm_ws_kernel<128,128> (Cholesky trailing update A22 -= P P^T, lower "
@@ -719,8 +749,11 @@ def main():
     if skip_cpu:
         cpu = {"value": None, "unit": None, "cores": 0, "kind": "skipped",
                "sample": "--no-cpu" if a.no_cpu else "reported at N=1 only"}
-    elif a.workload in ("c5", "c3"):
+    elif a.workload == "c5":
         cpu = cpu_baseline("reference", n_s, TH_B)
+    elif a.workload == "c3":
+        from oracle import oracle
+        cpu = cpu_c3_sample(oracle.reference() or oracle.port(), n_s)[0]
     if skip_cpu:
         pass
     elif a.workload == "c2":
