@@ -310,6 +310,7 @@ def bcm_parity(cg, torch, dist):
     ll, g = b.loglik_and_gradient()
     mu, var = b.compute_BCM_test_means_and_var(d["Xtest"][:gold["m"]])
     in_lib = bool(getattr(b, "_in_library", False))
+    kind = b.exchange_kind
     b.close()
     gref = np.array(gold["grad"])
     e = {"ll": abs(ll - gold["ll"]) / abs(gold["ll"]),
@@ -324,7 +325,8 @@ def bcm_parity(cg, torch, dist):
         worst = [float(v) for v in t.tolist()]
     return {"parity_ok_all_ranks": worst[4] == 0.0, "golden": "tests/golden/golden_c4.json (unmodified reference)",
             "max_rel_err_over_ranks": {"ll": worst[0], "grad": worst[1], "mean": worst[2], "var": worst[3]},
-            "tolerance": {"ll": 1e-9, "grad": 1e-9, "mean": 1e-8, "var": 1e-8}, "exchange_inside_library": in_lib}
+            "tolerance": {"ll": 1e-9, "grad": 1e-9, "mean": 1e-8, "var": 1e-8}, "exchange_inside_library": in_lib,
+            "exchange": kind}
 
 
 def extra_c4(cg, torch, dist, flush, m=10000, reps=6, experts=16, prefix="c4"):

@@ -85,6 +85,7 @@ SIGNATURES = {
     "cugp_bcm_comm_init_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "cugp_bcm_has_comm": (C.c_int, [C.c_void_p]),
     "cugp_bcm_collectives": (C.c_long, [C.c_void_p]),
+    "cugp_bcm_exchange_kind": (C.c_int, [C.c_void_p]),
     "cugp_bcm_loglik_grad": (C.c_int, [C.c_void_p, C.c_int, dp]),
     "cugp_shardstream_open_files": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                               C.c_size_t, C.POINTER(C.c_void_p)]),

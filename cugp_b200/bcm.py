@@ -77,6 +77,10 @@ class _CudaLocal:
     def collectives(self) -> int:
         return int(lib().cugp_bcm_collectives(self._h))
 
+    def exchange_kind(self) -> str:
+        """How the library's exchange step runs: 'none', 'nccl' or 'peer_memory' (csrc/peerxchg.cu)."""
+        return ("none", "nccl", "peer_memory")[int(lib().cugp_bcm_exchange_kind(self._h))]
+
     def set_theta(self, th):
         check(lib().cugp_bcm_set_loghyper(self._h, ptr(th)))
 
@@ -177,6 +181,13 @@ class BCM:
     @exchanges.setter
     def exchanges(self, v):
         self._exchanges = v
+
+    @property
+    def exchange_kind(self) -> str:
+        """'peer_memory' / 'nccl' (inside the library), 'torch' (the caller's process group) or 'none' (one rank)."""
+        if self._in_library:
+            return self._local.exchange_kind()
+        return "none" if self.world == 1 else "torch"
 
     def close(self):
         if getattr(self, "_local", None) is not None and hasattr(self._local, "close"):

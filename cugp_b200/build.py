@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libcugp.so")
-SOURCES = ["gemm_dmma.cu", "kernels.cu", "cholstep.cu", "gp.cu", "capi.cu", "shardstream.cu", "probe.cu", "optim.cpp"]
+SOURCES = ["gemm_dmma.cu", "kernels.cu", "cholstep.cu", "gp.cu", "capi.cu", "peerxchg.cu", "shardstream.cu", "probe.cu",
+           "optim.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -19,6 +19,7 @@
 
 #include "capi_internal.h"
 #include "cholstep.cuh"
+#include "peerxchg.cuh"
 #include "gp.cuh"
 #include "optim.h"
 
@@ -94,6 +95,10 @@ static void upload(cugp_covsum* h, const double* X, const double* y) {
         h->have_host = true;
     }
 }
+
+// BCM exchange over NVLink peer memory instead of ncclAllReduce where the ranks could set it up (tuning key
+// bcm_peer_exchange; must be the same on every rank)
+static int g_bcm_peer = 1;
 
 extern "C" {
 
@@ -184,6 +189,10 @@ int cugp_set_tuning(const char* key, long value) {
     if (std::strcmp(key, "kinv_group") == 0) {
         if (value < 1) return CUGP_ERR_INVALID;
         set_kinv_group((int)value);
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "bcm_peer_exchange") == 0) {   // same value on every rank (it selects the collective)
+        g_bcm_peer = value != 0;
         return CUGP_OK;
     }
     if (std::strcmp(key, "fused_panel") == 0) {
@@ -642,6 +651,7 @@ struct NcclApi {
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclGetErrorString) GetErrorString = nullptr;
     bool ok = false;
@@ -659,9 +669,10 @@ NcclApi& nccl_api() {
         a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
         a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
         a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+        a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
         a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
         a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString;
+        a.ok = a.GetUniqueId && a.CommInitRank && a.AllReduce && a.AllGather && a.CommDestroy && a.GetErrorString;
         if (!a.ok) a.why = "libnccl.so.2 lacks a required symbol";
         return a;
     }();
@@ -712,9 +723,11 @@ struct cugp_bcm {
     int xt_m = 0, xt_cap = 0;
     cudaStream_t st = nullptr;
     ncclComm_t comm = nullptr;
+    PeerExchange px;             // the exchange over NVLink peer memory (set up behind the communicator when it can be)
     long collectives = 0;
     ~cugp_bcm() {
         if (st) cudaStreamSynchronize(st);
+        peer_xchg_close(px);
         if (comm && nccl_api().ok) nccl_api().CommDestroy(comm);
         for (auto& g : groups) untrack(g.gp.get());
         groups.clear();
@@ -827,6 +840,60 @@ static void bcm_allreduce(cugp_bcm* h, double* buf, size_t count) {
     CUGP_NCCL(nccl_api().AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->st));
     h->collectives++;
 }
+// The exchange step of one operation: `planes` x `rows` doubles summed over the ranks in place.  Over peer memory when the
+// handle has it (one kernel that also finishes the operation: sums to `host_out`, PoE finalisation to `fin`; returns true),
+// else ncclAllReduce (returns false: the caller finishes with its own launches).  Same choice on every rank: it only
+// depends on the agreed set-up, the tuning key and the payload size.
+static bool bcm_exchange(cugp_bcm* h, double* buf, int planes, int rows, double* host_out, double* fin) {
+    if (h->world == 1) return false;
+    if (g_bcm_peer && h->px.ready && (size_t)planes * rows <= h->px.cap) {
+        launch_peer_allreduce(h->px, buf, planes, rows, host_out, fin, h->st);
+        h->collectives++;
+        return true;
+    }
+    bcm_allreduce(h, buf, (size_t)planes * rows);
+    return false;
+}
+static void bcm_exchange_check(cugp_bcm* h) {   // after the stream has been synchronised
+    if (h->px.err && *h->px.err) {
+        *h->px.err = 0;
+        set_last_error("BCM exchange over peer memory: a rank did not arrive (rank %d of %d)", h->rank, h->world);
+        throw CudaError{cudaErrorLaunchTimeout, __FILE__, __LINE__};
+    }
+}
+// Peer-memory set-up behind a fresh communicator: every rank exports one buffer (CUDA IPC), the handles travel by
+// ncclAllGather, and the ranks agree (ncclAllReduce min) that EVERYONE could map everyone -- else nobody uses it.
+static void bcm_peer_setup(cugp_bcm* h) {
+    peer_xchg_close(h->px);
+    if (h->world > PeerExchange::kMaxWorld) return;
+    constexpr size_t kCap = 65536;   // doubles per rank and parity: predictions of up to 32768 points, 8 MB at 8 ranks
+    cudaIpcMemHandle_t mine;
+    peer_xchg_alloc(h->px, h->rank, h->world, kCap, &mine);
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    unsigned char* dev = nullptr;
+    CUGP_CUDA(cudaMalloc((void**)&dev, hb * h->world + sizeof(int)));
+    std::vector<cudaIpcMemHandle_t> all(h->world);
+    bool ok = false;
+    try {
+        CUGP_CUDA(cudaMemcpyAsync(dev + hb * h->rank, &mine, hb, cudaMemcpyHostToDevice, h->st));
+        CUGP_NCCL(nccl_api().AllGather(dev + hb * h->rank, dev, hb, ncclChar, h->comm, h->st));
+        CUGP_CUDA(cudaMemcpyAsync(all.data(), dev, hb * h->world, cudaMemcpyDeviceToHost, h->st));
+        CUGP_CUDA(cudaStreamSynchronize(h->st));
+        int mine_ok = peer_xchg_open(h->px, all.data()) ? 1 : 0, all_ok = 0;
+        int* flag = reinterpret_cast<int*>(dev + hb * h->world);
+        CUGP_CUDA(cudaMemcpyAsync(flag, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, h->st));
+        CUGP_NCCL(nccl_api().AllReduce(flag, flag, 1, ncclInt32, ncclMin, h->comm, h->st));
+        CUGP_CUDA(cudaMemcpyAsync(&all_ok, flag, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CUGP_CUDA(cudaStreamSynchronize(h->st));
+        ok = all_ok == 1;
+    } catch (...) {
+        cudaFree(dev);
+        peer_xchg_close(h->px);
+        throw;
+    }
+    cudaFree(dev);
+    if (!ok) peer_xchg_close(h->px);
+}
 
 #define CUGP_CATCH_NCCL                                                                                       \
     }                                                                                                         \
@@ -930,12 +997,15 @@ int cugp_bcm_comm_init(cugp_bcm* h, const unsigned char id[CUGP_NCCL_ID_BYTES]) 
     }
     DeviceGuard dg(h->device);
     if (h->comm) {
+        CUGP_CUDA(cudaStreamSynchronize(h->st));
+        peer_xchg_close(h->px);
         nccl_api().CommDestroy(h->comm);
         h->comm = nullptr;
     }
     ncclUniqueId u;
     std::memcpy(&u, id, sizeof(u));
     CUGP_NCCL(nccl_api().CommInitRank(&h->comm, h->world, u, h->rank));
+    if (g_bcm_peer) bcm_peer_setup(h);
     return CUGP_OK;
     CUGP_CATCH_NCCL
 }
@@ -979,6 +1049,10 @@ int cugp_bcm_comm_init_file(cugp_bcm* h, const char* path, int timeout_s) {
 }
 int cugp_bcm_has_comm(cugp_bcm* h) { return h && h->comm ? 1 : 0; }
 long cugp_bcm_collectives(cugp_bcm* h) { return h ? h->collectives : 0; }
+int cugp_bcm_exchange_kind(cugp_bcm* h) {
+    if (!h || h->world == 1 || !h->comm) return 0;
+    return g_bcm_peer && h->px.ready ? 2 : 1;
+}
 
 // (LL, g0, g1, g2) summed over this rank's experts: every group's evaluation is queued first, ONE wait at the end.
 static void bcm_eval_enqueue(cugp_bcm* h, int want_grad) {
@@ -1013,8 +1087,13 @@ int cugp_bcm_loglik_grad(cugp_bcm* h, int want_grad, double out4[4]) {
     if (!h || !out4) return CUGP_ERR_INVALID;
     DeviceGuard dg(h->device);
     bcm_eval_enqueue(h, want_grad);
-    bcm_allreduce(h, h->red4, 4);
-    bcm_eval_collect(h, out4);
+    if (bcm_exchange(h, h->red4, 1, 4, h->hred4, nullptr)) {   // the kernel wrote the sums to the pinned host words
+        CUGP_CUDA(cudaStreamSynchronize(h->st));
+        bcm_exchange_check(h);
+        for (int k = 0; k < 4; k++) out4[k] = h->hred4[k];
+    } else {
+        bcm_eval_collect(h, out4);
+    }
     return CUGP_OK;
     CUGP_CATCH_NCCL
 }
@@ -1107,11 +1186,12 @@ int cugp_bcm_predict(cugp_bcm* h, const double* Xtest, int m, double* mean, doub
     DeviceGuard dg(h->device);
     ensure_pq(h, m);
     bcm_moments(h, Xtest, m, h->PQ, [&] {
-        bcm_allreduce(h, h->PQ, (size_t)2 * m);
-        launch_poe_finalize(h->PQ, m, h->PQ + 2 * (size_t)m, h->PQ + 3 * (size_t)m, h->st);
+        if (!bcm_exchange(h, h->PQ, 2, m, nullptr, h->PQ + 2 * (size_t)m))
+            launch_poe_finalize(h->PQ, m, h->PQ + 2 * (size_t)m, h->PQ + 3 * (size_t)m, h->st);
         CUGP_CUDA(cudaMemcpyAsync(h->hfin, h->PQ + 2 * (size_t)m, (size_t)2 * m * 8, cudaMemcpyDeviceToHost, h->st));
     });
     CUGP_CUDA(cudaStreamSynchronize(h->st));
+    bcm_exchange_check(h);
     std::memcpy(mean, h->hfin, (size_t)m * 8);
     std::memcpy(var, h->hfin + m, (size_t)m * 8);
     return CUGP_OK;

@@ -183,7 +183,12 @@ int cugp_bcm_comm_init(cugp_bcm *h, const unsigned char id[CUGP_NCCL_ID_BYTES]);
  * fresh for every communicator.  What include/cugp_shim/BCM.h uses under CUGP_RANK / CUGP_WORLD / CUGP_NCCL_ID_FILE. */
 int cugp_bcm_comm_init_file(cugp_bcm *h, const char *path, int timeout_s);
 int cugp_bcm_has_comm(cugp_bcm *h);        /* 1 once a communicator exists */
-long cugp_bcm_collectives(cugp_bcm *h);    /* NCCL collectives issued so far (one per operation) */
+long cugp_bcm_collectives(cugp_bcm *h);    /* exchange steps issued so far (one per operation) */
+/* How the exchange step runs: 0 = none (world 1 / no communicator), 1 = ncclAllReduce, 2 = one-shot allreduce over NVLink
+ * peer memory, fused with the finalisation (csrc/peerxchg.cu; set up by cugp_bcm_comm_init when every rank can map every
+ * other rank's buffer through CUDA IPC -- otherwise, and for payloads above 65536 doubles, NCCL).  Replaces the socket
+ * exchange of cuda_scalingdist/main.cpp:109-160. */
+int cugp_bcm_exchange_kind(cugp_bcm *h);
 /* BCM::get_BCM_loglikelihood + get_BCM_gradient_hyper (BCM.cpp:153-198) over ALL experts: local sums, then ONE
  * ncclAllReduce(sum, f64, 4) behind them on the same stream; out4 = (LL, g0, g1, g2), identical on every rank. */
 int cugp_bcm_loglik_grad(cugp_bcm *h, int want_grad, double out4[4]);

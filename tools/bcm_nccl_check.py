@@ -38,7 +38,13 @@ for name, c in gold.items():
         e_v = float(np.max(np.abs(var - c["var"]) / np.abs(c["var"])))
         line += f" mean relerr {e_m:.2e} var relerr {e_v:.2e}"
         good = good and e_m <= 1e-8 and e_v <= 1e-8
-    line += f" exchanges={b.exchanges}" + ("  OK" if good else "  FAIL")
+    # every rank must hold the SAME bits after the exchange (rank-ordered sums over peer memory; NCCL gives that too)
+    mine = torch.tensor([ll, *g], dtype=torch.float64, device="cuda")
+    ref0 = mine.clone()
+    dist.broadcast(ref0, src=0)
+    same = bool(torch.equal(mine, ref0))
+    good = good and same
+    line += f" exchange={b.exchange_kind} same_bits_as_rank0={same} exchanges={b.exchanges}" + ("  OK" if good else "  FAIL")
     print(line, flush=True)
     ok = ok and good
     b.close()
