@@ -195,6 +195,14 @@ int cugp_set_tuning(const char* key, long value) {
         g_bcm_peer = value != 0;
         return CUGP_OK;
     }
+    if (std::strcmp(key, "step_split_ctas") == 0) {
+        set_step_split_ctas((int)value);
+        return CUGP_OK;
+    }
+    if (std::strcmp(key, "panel_lookahead") == 0) {
+        set_panel_lookahead(value != 0);
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "fused_panel") == 0) {
         set_fused_panel(value != 0);
         return CUGP_OK;

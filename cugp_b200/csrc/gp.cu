@@ -88,7 +88,7 @@ int potrf_outer_width(int n) {
     // measured with look-ahead (profiles/r1_cholesky_nb_sweep.txt): wider panels only pay once the trailing update
     // dominates the chain of diagonal blocks
     if (n >= 24576) return 1024;
-    if (n >= 9000) return 512;
+    if (n >= 6000) return 512;   // (round 2, look-ahead inside the panel: 512 also wins at 6000 and 8192, profiles/r2_panel_lookahead.txt)
     if (n >= 5000) return 256;
     return kDiag;
 }
@@ -108,6 +108,11 @@ void set_fused_gemm_cap(int v) { g_fused_gemm_cap = v; bump_tuning_epoch(); }
 static int g_kinv_group = 1;   // identity-row path: K^-1 accumulated every this many block columns; > 1 measured slower
 // (profiles/r2_kinv_stream.txt: the bigger bursts delay U2 and the last one cannot hide behind the chain)
 void set_kinv_group(int v) { g_kinv_group = v; bump_tuning_epoch(); }
+static int g_split_ctas = 100;   // the step's row tiles as a second launch (after DIAG, no waiting CTAs) above this many CTAs; 0: the SM
+// count (profiles/r2_panel_lookahead.txt: n = 10000 13.26 -> 13.02 ms, 8192 8.24 -> 8.10; chain-bound sizes stay below it)
+void set_step_split_ctas(int v) { g_split_ctas = v; bump_tuning_epoch(); }
+static int g_panel_lookahead = 1;   // wide outer panels: look-ahead inside the panel too (profiles/r2_panel_lookahead.txt)
+void set_panel_lookahead(int v) { g_panel_lookahead = v; bump_tuning_epoch(); }
 static int g_fused_panel = 1;   // outer width > 128: the diagonal block + TRSM of every 128-column block as the fused step
 void set_fused_panel(int v) { g_fused_panel = v; bump_tuning_epoch(); }
 
@@ -128,7 +133,7 @@ static void potrf_panel(double* A, int64_t ld, int64_t sA, int n, int nrows, int
         if (fused) {
             // diagonal block (slab factorisation, 32x32 inverses) and the TRSM of every row below in the fused step kernel
             // (cholstep.cu) without its prologue: one launch while its CTAs fit the chip together, else two
-            const bool split = (int64_t)batch * chol_step_ctas(n, nrows, j0, batch) > sms;
+            const bool split = (int64_t)batch * chol_step_ctas(n, nrows, j0, batch) > (g_split_ctas > 0 ? g_split_ctas : sms);
             if (!split) {
                 launch_chol_step(A, ld, sA, n, nrows, j0, fx->pub, logdet_part, nblk, fx->sync, 0, batch, st, 0);
                 if (launches) ++*launches;
@@ -249,7 +254,7 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
     auto rows_at = [&](int Jend) { return base_rows + std::min(id_rows, Jend); };
     int widest = 0;
     for (int J0 = 0; J0 < n; J0 += kDiag) widest = std::max(widest, chol_step_ctas(n, rows_at(std::min(n, J0 + kDiag)), J0, batch));
-    const bool split = (int64_t)batch * widest > sms;
+    const bool split = (int64_t)batch * widest > (g_split_ctas > 0 ? g_split_ctas : sms);
     auto step = [&](int J0, int prologue, cudaStream_t s) {
         const int nr = rows_at(std::min(n, J0 + kDiag));
         if (!split) {
@@ -351,6 +356,23 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
     }
     const int npanels = (int)P.size();
     auto pend = [&](int J) { return J + 1 < npanels ? P[J + 1] : tail; };   // right edge of panel J (tail == n without a tail)
+    // One outer panel.  With the fused step: the panel is itself a (tall) factorisation of outer width 128 -- the chain of
+    // block steps (each applying the previous block column to its own, `prologue`) on the inner stream, the in-panel
+    // trailing updates on the panel's stream: the same look-ahead one level down, ~35 instead of ~70 us per 128 columns.
+    auto panel = [&](int J0, int Jend, cudaStream_t s) {
+        if (fpanel && g_panel_lookahead && la && la->st_inner) {   // (look-ahead off: potrf_fused runs it on one stream)
+            FusedCtx sub = *fx;
+            sub.sync = fx->sync + (int64_t)(J0 / kDiag) * 4;
+            PotrfLookahead in;
+            in.st2 = la->st_inner;
+            in.ev.swap(la->ev_inner);
+            potrf_fused(A + (int64_t)J0 * (ld + 1), ld, sA, Jend - J0, nrows - J0, invd, sInvd, logdet_part + J0 / kDiag, nblk,
+                        cdiv(Jend - J0, kDiag), batch, s, launches, nullptr, &in, &sub);
+            in.ev.swap(la->ev_inner);
+            return;
+        }
+        potrf_panel(A, ld, sA, n, nrows, J0, Jend, invd, sInvd, logdet_part, nblk, batch, s, launches, fx);
+    };
     auto run_tail = [&] {
         if (tail >= n) return;
         FusedCtx sub = *fx;
@@ -361,7 +383,7 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
     if (!la || !la->st2 || npanels < 3 || !lookahead_enabled()) {
         for (int J = 0; J < npanels; J++) {
             const int J0 = P[J], Jend = std::min(n, pend(J));
-            potrf_panel(A, ld, sA, n, nrows, J0, Jend, invd, sInvd, logdet_part, nblk, batch, st, launches, fx);
+            panel(J0, Jend, st);
             // trailing update: A[Jend:, Jend:] -= P P^T with P = L[Jend:, J0:Jend], lower tiles, K = outer width
             potrf_trailing(A, ld, sA, nrows, J0, Jend, Jend, n, batch, st, launches, prof);
         }
@@ -387,7 +409,7 @@ void potrf_blocked(double* A, int64_t ld, int64_t sA, int n, double* invd, int64
         const int J0 = P[J], Jend = std::min(n, pend(J));
         // the last two-level panel before a fused tail updates ALL remaining columns on the panel stream
         const int Jend2 = J + 1 < npanels ? std::min(n, pend(J + 1)) : n;
-        potrf_panel(A, ld, sA, n, nrows, J0, Jend, invd, sInvd, logdet_part, nblk, batch, s2, launches, fx);
+        panel(J0, Jend, s2);
         CUGP_CUDA(cudaEventRecord(evP(J), s2));
         if (Jend >= n) break;
         if (J >= 1) CUGP_CUDA(cudaStreamWaitEvent(s2, evU(J - 1), 0));
@@ -576,6 +598,7 @@ GpBatch::GpBatch(int B_, int n_, int d_, cudaStream_t stream) : B(B_), n(n_), d(
         int lo = 0, hi = 0;  // the panel stream of the look-ahead Cholesky gets the highest priority
         CUGP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CUGP_CUDA(cudaStreamCreateWithPriority(&la.st2, cudaStreamNonBlocking, hi));
+        CUGP_CUDA(cudaStreamCreateWithPriority(&la.st_inner, cudaStreamNonBlocking, hi));
     }
     const size_t bn = (size_t)B * n;
     dalloc(X, bn * dp);
@@ -611,6 +634,11 @@ GpBatch::~GpBatch() {
         cudaStreamSynchronize(la.st2);
         cudaStreamDestroy(la.st2);
     }
+    if (la.st_inner) {
+        cudaStreamSynchronize(la.st_inner);
+        cudaStreamDestroy(la.st_inner);
+    }
+    for (cudaEvent_t e : la.ev_inner) cudaEventDestroy(e);
     if (st3) {
         cudaStreamSynchronize(st3);
         cudaStreamDestroy(st3);

@@ -17,6 +17,10 @@ struct PotrfLookahead {
     cudaStream_t st2 = nullptr;
     std::vector<cudaEvent_t> ev;
     bool panel_events = false;   // the last potrf_blocked call took the look-ahead path: ev[2J] = "panel J is final"
+    // second level (wide outer panels): the chain of fused block steps INSIDE a panel runs on its own high-priority
+    // stream while the panel's stream applies the in-panel trailing updates
+    cudaStream_t st_inner = nullptr;
+    std::vector<cudaEvent_t> ev_inner;
 };
 
 // What the fused block-step path of potrf_blocked needs / reports (cholstep.cu).
@@ -178,6 +182,8 @@ void set_adaptive_nb(int v);  // 1 (default 0: measured slower): outer width by 
 void set_kinv_stream(int v);   // 1: K^-1 accumulation of the identity-row path on its own stream (default 0: measured slower)
 void set_fused_gemm_cap(int v);
 void set_kinv_group(int v);
+void set_step_split_ctas(int v);
+void set_panel_lookahead(int v);   // 1 (default): look-ahead inside wide outer panels as well
 void set_fused_panel(int v);  // 1 (default): wider outer panels also factor their 128-column blocks with the fused step
 void set_fused_step(int v); // 1 (default): one fused launch per 128-column block step when the outer width is 128
 // Tuning epoch: bumped by every tuning change so cached graphs are re-captured.  graph_max_n: largest n whose launch
