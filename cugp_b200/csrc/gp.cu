@@ -73,7 +73,9 @@ void set_fused_max_batch(int v) { g_fused_max_batch = v; bump_tuning_epoch(); }
 // Identity rows: for small n the factorisation carries n more appended rows that start as I and end as L^-T -- the inverse
 // of the factor costs no launch chain of its own (the TRTRI recursion is 12 dependent launches, 310 us at n = 1500 against
 // 420 us for the factorisation itself).  The row tiles of the fused step do the extra work in the diagonal CTA's shadow.
-static int g_idrows_max_n = 2048;
+// Bound (profiles/r2_idrows_bound.txt, LL + gradient): n = 2500 1.54 -> 1.21 ms, 3000 2.15 -> 1.87, 3500 2.87 -> 2.78, 4096 3.66 -> 3.96 --
+// from there the rank-128 updates of the (2n+1) x n array stream it through HBM once per block column.
+static int g_idrows_max_n = 3500;
 void set_idrows_max_n(int n) { g_idrows_max_n = n; bump_tuning_epoch(); }
 int idrows_max_n() { return g_idrows_max_n; }
 static int g_potrf_nb = 0;  // 0: by size; otherwise forced (cugp_set_tuning("potrf_nb", v) or CUGP_POTRF_NB)

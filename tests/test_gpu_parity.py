@@ -230,6 +230,7 @@ def test_overlapped_inverse_matches_sequential(n, B):
     thetas = [[3.762111, -1.152105, -0.384461], [2.0, 2.0, 2.0], [3.0, 0.5, -1.0]]
     res = {}
     try:
+        lib().cugp_set_tuning(b"idrows_max_n", 0)   # (below 3500 the identity rows would take over: not the path under test)
         for mode, max_n, cap in (("seq", 0, 64), ("ovl64", 8192, 64), ("ovl8", 8192, 8)):
             lib().cugp_set_tuning(b"overlap_inv_max_n", max_n)
             lib().cugp_set_tuning(b"overlap_inv_cap", cap)
@@ -256,6 +257,7 @@ def test_overlapped_inverse_matches_sequential(n, B):
     finally:
         lib().cugp_set_tuning(b"overlap_inv_max_n", OVERLAP_DEFAULT)
         lib().cugp_set_tuning(b"overlap_inv_cap", 148)
+        lib().cugp_set_tuning(b"idrows_max_n", 3500)
     for mode in ("ovl64", "ovl8"):
         for a, b_ in zip(res["seq"], res[mode]):
             assert np.array_equal(np.asarray(a[0]), np.asarray(b_[0])) or np.allclose(a[0], b_[0], rtol=1e-11, atol=0)
@@ -481,6 +483,49 @@ def test_loglik_then_grad_share_one_factorisation():
     assert g.compute_loglikelihood(X, y2) != g.compute_loglikelihood(X, y)   # changed data is noticed
 
 
+@pytest.mark.parametrize("n,B", [(900, 1), (1500, 2), (2600, 1), (3400, 1)])
+def test_identity_rows_match_the_inverse_chain(n, B):
+    """n <= 3500: L^-T and K^-1 leave the factorisation itself (n appended identity rows, 64-row tiles once the step is
+    wide; replayed as a graph up to 2048, direct launches above) against TRTRI + LAUUM after it (idrows_max_n = 0):
+    LL identical (same factor), gradient, alpha and predictions to rounding -- matrixops.cpp:383-435, covkernel.cpp:277-302."""
+    from cugp_b200.loaders import synthetic_sine
+    X, y = synthetic_sine(n * B + 9, 10, seed=n + B)
+    Xt = X[n * B:]
+    out = {}
+    try:
+        for mode, bound in (("chain", 0), ("idrows", 3500)):
+            lib().cugp_set_tuning(b"idrows_max_n", bound)
+            res = []
+            if B == 1:
+                g = cg.Covsum(n, 10)
+                g.set_data(X[:n], y[:n])
+                for th in (TH_B, [2.0, 2.0, 2.0], TH_B):          # the second and third evaluation take the learned path
+                    g.set_loghyperparam(th)
+                    res.append((g.loglik_resident(), g.grad_resident().copy()))
+                res.append(g.compute_test_means_and_variances(X[:n], y[:n], Xt))
+                g.close()
+            else:
+                b = cg.BCM(X[:n * B], y[:n * B], K=B, rank=0, world=1)
+                for th in (TH_B, [2.0, 2.0, 2.0], TH_B):
+                    b.set_BCM_log_hyperparam(th)
+                    ll, gr = b.loglik_and_gradient()
+                    res.append((ll, gr.copy()))
+                res.append(b.compute_BCM_test_means_and_var(Xt))
+                b.close()
+            out[mode] = res
+    finally:
+        lib().cugp_set_tuning(b"idrows_max_n", 3500)
+    for a, b_ in zip(out["chain"][:3], out["idrows"][:3]):
+        assert_ll(b_[0], a[0], 1e-12)
+        assert_grad(b_[1], a[1], 1e-10)
+    np.testing.assert_allclose(out["idrows"][3][0], out["chain"][3][0], rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(out["idrows"][3][1], out["chain"][3][1], rtol=1e-10)
+    assert_grad(out["idrows"][2][1], out["idrows"][0][1], 1e-10)    # same theta: first evaluation inverts afterwards, third carries the rows
+    if n <= 1000 and B == 1:                                        # and the oracle agrees (seconds on the CPU)
+        assert_ll(out["idrows"][0][0], PORT.loglik(X[:n], y[:n], TH_B), 1e-10)
+        assert_grad(out["idrows"][0][1], PORT.grad(X[:n], y[:n], TH_B), 1e-9)
+
+
 def test_cg_solve_replays_reference_log():
     """cuda_bettersinglenode_ver2/REF: LL trajectory (6 digits) and optimum of the 128x2 problem."""
     d = load_data("si128x2")
@@ -558,7 +603,7 @@ def test_inplace_inverse_matches_three_buffer_path(n):
         mu, var = g.compute_test_means_and_variances(X, y, X[:5])
     finally:
         lib().cugp_set_tuning(b"inplace_inverse_min_n", 60000)
-        lib().cugp_set_tuning(b"idrows_max_n", 2048)
+        lib().cugp_set_tuning(b"idrows_max_n", 3500)
     assert_ll(ll1, ll0, 1e-11)
     assert ll2 == ll1
     assert_grad(g1, g0, 1e-9)
