@@ -1063,15 +1063,16 @@ int cugp_bcm_exchange_kind(cugp_bcm* h) {
 }
 
 // (LL, g0, g1, g2) summed over this rank's experts: every group's evaluation is queued first, ONE wait at the end.
-static void bcm_eval_enqueue(cugp_bcm* h, int want_grad) {
+static void bcm_eval_enqueue(cugp_bcm* h, int want_grad, bool sums_later = false) {
     int acc = 0;
     for (auto& g : h->groups) {  // groups are in ascending expert order, experts ascending inside
         g.gp->eval_enqueue(want_grad != 0);
+        if (sums_later) continue;   // (one group: the exchange kernel forms the local sums itself)
         bcm_sum4_kernel<<<1, 32, 0, h->st>>>(g.gp->scal, g.gp->gradout, g.gp->B, want_grad, h->red4, acc);
         g.gp->launches++;
         acc = 1;
     }
-    if (!acc) CUGP_CUDA(cudaMemsetAsync(h->red4, 0, 4 * 8, h->st));
+    if (!acc && !sums_later) CUGP_CUDA(cudaMemsetAsync(h->red4, 0, 4 * 8, h->st));
     CUGP_CUDA(cudaGetLastError());
 }
 static void bcm_eval_collect(cugp_bcm* h, double out4[4]) {
@@ -1094,6 +1095,19 @@ int cugp_bcm_loglik_grad(cugp_bcm* h, int want_grad, double out4[4]) {
     CUGP_TRY
     if (!h || !out4) return CUGP_ERR_INVALID;
     DeviceGuard dg(h->device);
+    if (h->world > 1 && g_bcm_peer && h->px.ready && h->groups.size() == 1) {
+        // one kernel: local sums over the experts, exchange over peer memory, rank-ordered total into pinned host words
+        bcm_eval_enqueue(h, want_grad, true);
+        GpBatch* gp = h->groups[0].gp.get();
+        PeerPresum pre{gp->scal, want_grad ? gp->gradout : nullptr, gp->B};
+        launch_peer_allreduce(h->px, h->red4, 1, 4, h->hred4, nullptr, h->st, &pre);
+        gp->launches++;
+        h->collectives++;
+        CUGP_CUDA(cudaStreamSynchronize(h->st));
+        bcm_exchange_check(h);
+        for (int k = 0; k < 4; k++) out4[k] = h->hred4[k];
+        return CUGP_OK;
+    }
     bcm_eval_enqueue(h, want_grad);
     if (bcm_exchange(h, h->red4, 1, 4, h->hred4, nullptr)) {   // the kernel wrote the sums to the pinned host words
         CUGP_CUDA(cudaStreamSynchronize(h->st));

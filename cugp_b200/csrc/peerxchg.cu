@@ -27,6 +27,9 @@ struct XchgArgs {
     double* host_out;
     double* fin;
     int* err;
+    const double* pre_scal;
+    const double* pre_grad;
+    int pre_n;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -45,6 +48,15 @@ __global__ void __launch_bounds__(XT) peer_allreduce_kernel(const XchgArgs a) {
     const int per = (a.rows + gridDim.x - 1) / gridDim.x;
     const int lo = b * per, hi = min(a.rows, lo + per);
     const size_t slot = (size_t)(a.parity * a.world + a.rank) * a.cap;
+    if (a.pre_scal) {   // (one block, rows == 4) the local sums first, in expert order
+        if (tid < 4) {
+            double s = 0.0;
+            for (int e = 0; e < a.pre_n; e++)
+                s += tid == 0 ? a.pre_scal[e * 4 + 2] : (a.pre_grad ? a.pre_grad[e * 3 + tid - 1] : 0.0);
+            a.buf[tid] = s;
+        }
+        __syncthreads();
+    }
     // 1. my chunk into my slot of every rank's buffer
     for (int pl = 0; pl < a.planes; pl++)
         for (int t = lo + tid; t < hi; t += XT) {
@@ -143,9 +155,11 @@ void peer_xchg_close(PeerExchange& x) {
     x.ready = false;
 }
 
-void launch_peer_allreduce(PeerExchange& x, double* buf, int planes, int rows, double* host_out, double* fin, cudaStream_t st) {
+void launch_peer_allreduce(PeerExchange& x, double* buf, int planes, int rows, double* host_out, double* fin, cudaStream_t st,
+                           const PeerPresum* presum) {
     if (!x.ready || planes < 1 || planes > 2 || rows <= 0 || (size_t)planes * rows > x.cap || (fin && planes != 2))
         throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};
+    if (presum && (planes != 1 || rows != 4)) throw CudaError{cudaErrorInvalidValue, __FILE__, __LINE__};
     XchgArgs a{};
     const size_t fb = PeerExchange::flag_bytes(x.world);
     for (int r = 0; r < x.world; r++) {
@@ -155,7 +169,10 @@ void launch_peer_allreduce(PeerExchange& x, double* buf, int planes, int rows, d
     x.seq++;
     a.rank = x.rank; a.world = x.world; a.parity = (int)(x.seq & 1); a.seq = x.seq; a.cap = x.cap;
     a.buf = buf; a.planes = planes; a.rows = rows; a.host_out = host_out; a.fin = fin; a.err = x.err;
-    const int blocks = std::max(1, std::min(PeerExchange::kMaxBlocks, cdiv(rows, 2 * XT)));
+    if (presum) {
+        a.pre_scal = presum->scal; a.pre_grad = presum->grad; a.pre_n = presum->nexp;
+    }
+    const int blocks = std::max(1, std::min(PeerExchange::kMaxBlocks, cdiv(rows, XT)));   // (a function of `rows` only: same grid on every rank)
     peer_allreduce_kernel<<<blocks, XT, 0, st>>>(a);
     CUGP_CUDA(cudaGetLastError());
 }

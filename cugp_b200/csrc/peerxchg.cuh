@@ -33,6 +33,14 @@ void peer_xchg_close(PeerExchange& x);
 //   fin      : optional, planes == 2 only: the product-of-experts finalisation of BCM.cpp:56-60 on the summed moments,
 //              fin[t] = Q/P, fin[rows + t] = 1/P
 // Every rank must call with the same (planes, rows).  planes * rows <= x.cap.
-void launch_peer_allreduce(PeerExchange& x, double* buf, int planes, int rows, double* host_out, double* fin, cudaStream_t st);
+//   presum   : optional (planes == 1, rows == 4): buf is first filled with (sum_b scal[4b+2], sum_b grad[3b+k]) over nexp
+//              experts in expert order -- the local (LL, gradient) sums of a BCM evaluation, without a launch of their own
+struct PeerPresum {
+    const double* scal;
+    const double* grad;   // null: no gradient (zeros)
+    int nexp;
+};
+void launch_peer_allreduce(PeerExchange& x, double* buf, int planes, int rows, double* host_out, double* fin, cudaStream_t st,
+                           const PeerPresum* presum = nullptr);
 
 }  // namespace cugp

@@ -17,3 +17,6 @@ d=json.loads(sys.stdin.readline())
 print('  step ms', d['ms_per_step'], 'pts/s', d['value'], 'phases', d.get('phases'))"
 done
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29555 tools/bcm_nccl_check.py > gpurun_out/bcm_nccl_check_${NG}gpu.log 2>&1; echo "parity rc=$?"; grep -c OK gpurun_out/bcm_nccl_check_${NG}gpu.log
+# the exchange over peer memory against ncclAllReduce on the same handles, and the reference's own driver on two GPUs
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29556 tools/r2_peer_ab.py > gpurun_out/peer_ab_${NG}gpu.log 2>&1; echo "peer_ab rc=$?"; grep "exchange=\|relerr" gpurun_out/peer_ab_${NG}gpu.log
+timeout 600 python -m pytest tests/test_shim.py -m gpu -x -q -k two_gpus > gpurun_out/shim_2gpu.log 2>&1; echo "shim 2gpu rc=$?"; tail -2 gpurun_out/shim_2gpu.log
