@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
-for N in 1 2 4 8; do
+for N in ${NS:-1 2 4 8}; do
   [ $N -gt $NG ] && continue
   if [ $N -eq 1 ]; then
     timeout 300 python bench.py --workload c4 --gpus 1 --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_c4_${N}gpu.log 2> gpurun_out/bench_c4_${N}gpu.err
