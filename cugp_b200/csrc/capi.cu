@@ -203,6 +203,11 @@ int cugp_set_tuning(const char* key, long value) {
         set_panel_lookahead(value != 0);
         return CUGP_OK;
     }
+    if (std::strcmp(key, "gemm_big_min_tiles") == 0) {
+        set_gemm_big_min_tiles((int)value);
+        bump_tuning_epoch();
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "fused_panel") == 0) {
         set_fused_panel(value != 0);
         return CUGP_OK;

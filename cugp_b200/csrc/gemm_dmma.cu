@@ -401,6 +401,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + NPW) * 32, MINB) dgemm_ws
 
 static int g_raster_w = RASTER_W_DEFAULT;
 static int g_small_two = 1;   // 64 x 64 configuration: 1 = three stages, two CTAs per SM; 0 = four stages, one CTA per SM
+static int g_big_min_tiles = 2 * 148;   // 128x128 tiles from this many on (else 64x64, two CTAs per SM); tuning key gemm_big_min_tiles
 static int g_tiles_per_cta = 0;  // 0: by grid size; otherwise forced (cugp_set_tuning("gemm_tpc", v))
 
 template <int BM, int BN, int WARPS_M, int WARPS_N, int NSTAGE, bool A_KC, bool B_KC, int MINB>
@@ -476,8 +477,9 @@ int gemm_tile_m(GemmConfig cfg) { return cfg == GEMM_BIG ? 128 : 64; }
 GemmConfig pick_config(int M, int N, int batch, bool lower_tiles) {
     int64_t tm = cdiv(M, 128), tn = cdiv(N, 128);
     int64_t tiles = (lower_tiles ? tn * (tn + 1) / 2 + (tm - tn) * tn : tm * tn) * batch;
-    return tiles >= 2 * 148 ? GEMM_BIG : GEMM_SMALL;
+    return tiles >= g_big_min_tiles ? GEMM_BIG : GEMM_SMALL;
 }
+void set_gemm_big_min_tiles(int v) { g_big_min_tiles = v > 0 ? v : 2 * 148; }
 
 void launch_gemm(const GemmParams& p, bool a_kc, bool b_kc, GemmConfig cfg, cudaStream_t stream) {
     switch (cfg) {

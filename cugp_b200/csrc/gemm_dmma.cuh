@@ -48,7 +48,8 @@ GemmConfig pick_config(int M, int N, int batch, bool lower_tiles);
 int gemm_tile_m(GemmConfig cfg);
 // Tuning: tiles walked per CTA (0 = by grid size).
 void set_gemm_tiles_per_cta(int v);
-void set_gemm_small_two(int v);      // 64x64 configuration: 1 (default) three stages and two CTAs per SM, 0 four stages and one
+void set_gemm_small_two(int v);
+void set_gemm_big_min_tiles(int v);      // 64x64 configuration: 1 (default) three stages and two CTAs per SM, 0 four stages and one
 void set_gemm_raster_width(int v);   // tile columns per raster strip (0 = default)
 
 }  // namespace cugp
