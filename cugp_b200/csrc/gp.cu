@@ -135,7 +135,7 @@ static void potrf_panel(double* A, int64_t ld, int64_t sA, int n, int nrows, int
         if (fused) {
             // diagonal block (slab factorisation, 32x32 inverses) and the TRSM of every row below in the fused step kernel
             // (cholstep.cu) without its prologue: one launch while its CTAs fit the chip together, else two
-            const bool split = (int64_t)batch * chol_step_ctas(n, nrows, j0, batch) > (g_split_ctas > 0 ? g_split_ctas : sms);
+            const bool split = (int64_t)batch * chol_step_ctas(n, nrows, j0, batch) > (g_split_ctas > 0 && batch == 1 ? g_split_ctas : sms);
             if (!split) {
                 launch_chol_step(A, ld, sA, n, nrows, j0, fx->pub, logdet_part, nblk, fx->sync, 0, batch, st, 0);
                 if (launches) ++*launches;
@@ -256,7 +256,9 @@ static void potrf_fused(double* A, int64_t ld, int64_t sA, int n, int nrows, dou
     auto rows_at = [&](int Jend) { return base_rows + std::min(id_rows, Jend); };
     int widest = 0;
     for (int J0 = 0; J0 < n; J0 += kDiag) widest = std::max(widest, chol_step_ctas(n, rows_at(std::min(n, J0 + kDiag)), J0, batch));
-    const bool split = (int64_t)batch * widest > (g_split_ctas > 0 ? g_split_ctas : sms);
+    // (the lower bound only for a single matrix: three or four 1500-row experts per GPU lose 10-20 % with it,
+    // profiles/r2_panel_lookahead.txt)
+    const bool split = (int64_t)batch * widest > (g_split_ctas > 0 && batch == 1 ? g_split_ctas : sms);
     auto step = [&](int J0, int prologue, cudaStream_t s) {
         const int nr = rows_at(std::min(n, J0 + kDiag));
         if (!split) {
