@@ -56,7 +56,20 @@ void cugp_launch_count_reset(void);
  * one thread-block-cluster launch (default) or one launch per 128-row block; "graph_max_n": largest n whose
  * theta-independent launch chains (factorisation; inverse chain) are replayed as CUDA graphs (0 = never, default 2048);
  * "overlap_inv_max_n": largest n for which T = L^-1 is computed on a third stream while the factorisation advances
- * (0 = never, default 6144), "overlap_inv_cap": SMs those background GEMMs may occupy (default: all). */
+ * (0 = never, default 2800), "overlap_inv_cap": SMs those background GEMMs may occupy (default: all).
+ * Round 2 (defaults in brackets; every measured A/B is under profiles/r2_*.txt):
+ *   "fused_step" [1] one launch per 128-column block step (csrc/cholstep.cu), "fused_max_batch" [10] widest batch it serves,
+ *   "fused_panel" [1] / "panel_lookahead" [1] the same steps, as their own look-ahead chain, inside wider outer panels,
+ *   "step_rows_tile" [0 = by CTA count | 32 | 64] rows per row-tile CTA of the step, "step_split_ctas" [100, single matrices]
+ *   CTAs above which the step's row tiles are a second launch, "adaptive_nb" [0], "fused_gemm_cap" [0], "kinv_stream" [0],
+ *   "kinv_group" [1] scheduling variants that measured slower;
+ *   "idrows_max_n" [3500] largest n whose factorisation carries n identity rows (L^-T and K^-1 as by-products; read when a
+ *   handle is created), "inplace_inverse_min_n" [60000] smallest n whose inverse is formed over the factor in place,
+ *   "pred_chunk" [0 = by memory] test points per prediction chunk;
+ *   "gemm_small_two" [1] two 64x64 CTAs per SM, "gemm_big_min_tiles" [296] tiles from which the GEMM uses 128x128 tiles;
+ *   "cov_fast" [1] FMA distance / precomputed -1/(2 l^2) in the covariance kernels (0 = the reference's operation order);
+ *   "bcm_peer_exchange" [1] BCM exchange over NVLink peer memory when every rank could map every peer (0 = ncclAllReduce;
+ *   must be equal on all ranks). */
 int cugp_set_tuning(const char *key, long value);
 
 /* ---- Covsum (cpp_serial_gp/covkernel.h:3-38) ------------------------------------------------------ */
