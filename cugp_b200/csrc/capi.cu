@@ -208,6 +208,10 @@ int cugp_set_tuning(const char* key, long value) {
         bump_tuning_epoch();
         return CUGP_OK;
     }
+    if (std::strcmp(key, "id_init_sparse") == 0) {
+        set_id_init_sparse(value != 0);
+        return CUGP_OK;
+    }
     if (std::strcmp(key, "fused_panel") == 0) {
         set_fused_panel(value != 0);
         return CUGP_OK;

@@ -115,6 +115,8 @@ static int g_split_ctas = 100;   // the step's row tiles as a second launch (aft
 void set_step_split_ctas(int v) { g_split_ctas = v; bump_tuning_epoch(); }
 static int g_panel_lookahead = 1;   // wide outer panels: look-ahead inside the panel too (profiles/r2_panel_lookahead.txt)
 void set_panel_lookahead(int v) { g_panel_lookahead = v; bump_tuning_epoch(); }
+static int g_id_init_sparse = 1;   // identity rows / K^-1 accumulator: only the parts that are read, one launch
+void set_id_init_sparse(int v) { g_id_init_sparse = v; bump_tuning_epoch(); }
 static int g_fused_panel = 1;   // outer width > 128: the diagonal block + TRSM of every 128-column block as the fused step
 void set_fused_panel(int v) { g_fused_panel = v; bump_tuning_epoch(); }
 
@@ -804,10 +806,15 @@ void GpBatch::potrf_with_rhs() {
     auto body = [&] {
         launch_copy_rows(y, n, Kb + (int64_t)n * ld, mat_stride(), n, B, st);
         if (id) {
-            launch_init_identity(Tt(), ld, mat_stride(), n, B, st);
-            launches++;
-            for (int b = 0; b < B; b++)   // K^-1 is accumulated block column by block column during the factorisation
-                CUGP_CUDA(cudaMemsetAsync(Wb + (int64_t)b * mat_stride(), 0, (size_t)n * ld * sizeof(double), st));
+            if (g_id_init_sparse) {   // one launch, half the bytes (profiles/r2_kinv_stream.txt)
+                launch_init_idrows(Tt(), mat_stride(), Wb, mat_stride(), ld, n, B, st);
+                launches++;
+            } else {
+                launch_init_identity(Tt(), ld, mat_stride(), n, B, st);
+                launches++;
+                for (int b = 0; b < B; b++)   // K^-1 is accumulated block column by block column during the factorisation
+                    CUGP_CUDA(cudaMemsetAsync(Wb + (int64_t)b * mat_stride(), 0, (size_t)n * ld * sizeof(double), st));
+            }
         }
         FusedCtx fx{stepsync, steppub, id ? n : 0, id ? Wb : nullptr, false};
         if (id && g_kinv_stream) {

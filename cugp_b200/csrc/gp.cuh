@@ -184,6 +184,7 @@ void set_fused_gemm_cap(int v);
 void set_kinv_group(int v);
 void set_step_split_ctas(int v);
 void set_panel_lookahead(int v);   // 1 (default): look-ahead inside wide outer panels as well
+void set_id_init_sparse(int v);
 void set_fused_panel(int v);  // 1 (default): wider outer panels also factor their 128-column blocks with the fused step
 void set_fused_step(int v); // 1 (default): one fused launch per 128-column block step when the outer width is 128
 // Tuning epoch: bumped by every tuning change so cached graphs are re-captured.  graph_max_n: largest n whose launch

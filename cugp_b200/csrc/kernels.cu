@@ -961,6 +961,22 @@ __global__ void init_identity_kernel(double* R, int64_t ld, int64_t sR, int n) {
         row[c2] = make_double2(2 * c2 == i ? 1.0 : 0.0, 2 * c2 + 1 == i ? 1.0 : 0.0);
 }
 
+// Identity rows + K^-1 accumulator in one pass, and only what is ever read (gp.cu: potrf_with_rhs): row i of the identity
+// block from the start of the block column LEFT of its own (the step's prologue reads one block column back; everything
+// further left is never touched: the rows join at step i / 128), row i of the accumulator up to the end of its own
+// 128-column block (lower tiles of the rank-128 updates).
+__global__ void init_idrows_kernel(double* R, int64_t sR, double* W, int64_t sW, int64_t ld, int n) {
+    const int64_t b = blockIdx.z;
+    const int i = blockIdx.y;
+    const int cs = max(0, (i / kDiag - 1) * kDiag), ce = min((int)ld, (i / kDiag + 1) * kDiag);
+    double2* row = reinterpret_cast<double2*>(R + b * sR + (int64_t)i * ld);
+    double2* wrow = reinterpret_cast<double2*>(W + b * sW + (int64_t)i * ld);
+    for (int c2 = blockIdx.x * blockDim.x + threadIdx.x; c2 < ld / 2; c2 += gridDim.x * blockDim.x) {
+        if (2 * c2 >= cs) row[c2] = make_double2(2 * c2 == i ? 1.0 : 0.0, 2 * c2 + 1 == i ? 1.0 : 0.0);
+        if (2 * c2 < ce) wrow[c2] = make_double2(0.0, 0.0);
+    }
+}
+
 __global__ void __launch_bounds__(256) gemv_upper_kernel(const double* __restrict__ U, int64_t ld, int64_t sU, int n,
                                                          const double* __restrict__ z, int64_t sZ, double* alpha, int64_t sAlpha) {
     const int64_t b = blockIdx.y;
@@ -1300,6 +1316,12 @@ void launch_gemv_t(const double* T, int64_t ld, int64_t sT, int n, const double*
 void launch_init_identity(double* R, int64_t ld, int64_t sR, int n, int batch, cudaStream_t st) {
     if (n <= 0 || batch <= 0) return;
     init_identity_kernel<<<dim3(cdiv(ld / 2, 256), n, batch), 256, 0, st>>>(R, ld, sR, n);
+    CUGP_CUDA(cudaGetLastError());
+}
+
+void launch_init_idrows(double* R, int64_t sR, double* W, int64_t sW, int64_t ld, int n, int batch, cudaStream_t st) {
+    if (n <= 0 || batch <= 0) return;
+    init_idrows_kernel<<<dim3(cdiv(ld / 2, 256), n, batch), 256, 0, st>>>(R, sR, W, sW, ld, n);
     CUGP_CUDA(cudaGetLastError());
 }
 

@@ -78,6 +78,8 @@ void launch_gemv_t(const double* T, int64_t ld, int64_t sT, int n, const double*
                    double* scratch /* trsv_backward_scratch(n, batch) doubles */, int batch, cudaStream_t st);
 // rows [0, n) of R (row stride ld, batch stride sR) <- identity (every entry of the n x ld block is written)
 void launch_init_identity(double* R, int64_t ld, int64_t sR, int n, int batch, cudaStream_t st);
+// identity rows (R) and the zeroed lower 128-tiles of the K^-1 accumulator (W) in one launch, only the parts that are read
+void launch_init_idrows(double* R, int64_t sR, double* W, int64_t sW, int64_t ld, int n, int batch, cudaStream_t st);
 // alpha[i] = sum_{k >= i} U[i][k] z[k] for an upper-triangular row-major U (= L^-T): one warp per row, coalesced
 void launch_gemv_upper(const double* U, int64_t ld, int64_t sU, int n, const double* z, int64_t sZ, double* alpha, int64_t sAlpha,
                        int batch, cudaStream_t st);

@@ -65,6 +65,7 @@ void cugp_launch_count_reset(void);
  *   "kinv_group" [1] scheduling variants that measured slower;
  *   "idrows_max_n" [3500] largest n whose factorisation carries n identity rows (L^-T and K^-1 as by-products; read when a
  *   handle is created), "inplace_inverse_min_n" [60000] smallest n whose inverse is formed over the factor in place,
+ *   "id_init_sparse" [1] identity rows and K^-1 accumulator initialised in one launch, only where they are read,
  *   "pred_chunk" [0 = by memory] test points per prediction chunk;
  *   "gemm_small_two" [1] two 64x64 CTAs per SM, "gemm_big_min_tiles" [296] tiles from which the GEMM uses 128x128 tiles;
  *   "cov_fast" [1] FMA distance / precomputed -1/(2 l^2) in the covariance kernels (0 = the reference's operation order);
